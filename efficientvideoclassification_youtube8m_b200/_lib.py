@@ -1,0 +1,76 @@
+"""ctypes binding of libevc.so (include/evc.h).  There is no fallback: if the shared
+library is missing the import of any product module fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libevc.so")
+
+P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/evc.h
+SIGNATURES = {
+    "evc_version": [],
+    "evc_last_error": [],
+    "evc_launch_count": [],
+    "evc_frames_pack": [P, I, I, I, P, I, I, I, I, P, P, P],
+    "evc_num_frames_student": [P, I, I, I, P, P],
+    "evc_lstm_lengths": [P, I, I, I, I, P, P, P],
+    "evc_random_frame_index": [P, P, I, I, P, P],
+    "evc_random_sequence_index": [P, P, I, I, P, P],
+    "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
+    "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P],
+    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P],
+    "evc_state_pack": [P, P, P, P, I, I, P, P, P],
+    "evc_cast_bf16": [P, L, I, I, P, P],
+    "evc_fill_f32": [P, L, F, P],
+    "evc_moe_mix_fwd": [P, L, P, L, I, I, I, P, P, P, P],
+    "evc_moe_loss_bwd": [P, L, P, L, P, P, P, I, I, I, F, F, P, L, P, L, P, P],
+    "evc_rep_loss": [P, P, I, I, F, P, P, P],
+    "evc_colsum_bf16": [P, L, I, L, P, P],
+    "evc_sumsq": [P, P, F, L, P, P],
+    "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P],
+    "evc_topk": [P, I, I, I, P, P, P, P, P],
+}
+_RESTYPES = {"evc_last_error": C.c_char_p, "evc_launch_count": C.c_longlong}
+
+
+class EvcError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` from the repo root.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise EvcError(f"{what or 'libevc'} failed ({rc}): {lib.evc_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.evc_launch_count())

@@ -1,0 +1,207 @@
+// Host side of the tcgen05 GEMM family: tensor-map construction, launch, and the C-ABI entry
+// points evc_gemm_bf16 / evc_lstm_seq_fwd / evc_lstm_seq_bwd declared in include/evc.h.
+#include "evc_gemm.cuh"
+#include "evc_host.h"
+
+#include <cudaTypedefs.h>
+
+namespace evc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] with row pitch `pitch_elems`; box = box_inner x box_outer, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                     uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * 2) % 16 != 0)
+    return set_error(EVC_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return EVC_OK;
+}
+
+// logical A[M,K]: a_mn = 0 -> stored [M][K]; a_mn = 1 -> stored [K][M]
+static int make_tmap_a(CUtensorMap* m, const void* p, int a_mn, long long ld, int M, int K) {
+  return a_mn ? make_tmap(m, p, M, K, ld, 64, 64) : make_tmap(m, p, K, M, ld, 64, BM);
+}
+// logical B[K,N]: b_mn = 0 -> stored [N][K]; b_mn = 1 -> stored [K][N]
+static int make_tmap_b(CUtensorMap* m, const void* p, int b_mn, long long ld, int N, int K, int bn) {
+  return b_mn ? make_tmap(m, p, N, K, ld, 64, 64) : make_tmap(m, p, K, N, ld, 64, bn);
+}
+
+template <int A_MN, int B_MN, int BN, int EPI>
+static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& args,
+                  cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
+    configured = true;
+  }
+  const int work = args.tiles_m * args.tiles_n * args.split_k;
+  if (work <= 0) return EVC_OK;
+  const int grid = work < num_sms() ? work : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, args);
+  count_launch();
+  return check_launch("gemm_kernel");
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ generic GEMM
+static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M, int N,
+                      int K, void* C, int c_bf16, long long ldc, const float* bias, int split_k, int accumulate,
+                      cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "gemm: empty problem");
+  if (split_k < 1) split_k = 1;
+  if ((split_k > 1 || accumulate) && c_bf16) return set_error(EVC_ERR_ARG, "gemm: split-K/accumulate needs f32 C");
+  const int bn = (N > 128) ? 256 : 128;
+  GemmArgs g = {};
+  g.M = M; g.N = N;
+  g.tiles_m = ceil_div(M, BM);
+  g.tiles_n = ceil_div(N, bn);
+  g.kb_total = ceil_div(K, BK);
+  g.kb_a1 = g.kb_total;
+  g.kb_per_split = ceil_div(g.kb_total, split_k);
+  g.split_k = ceil_div(g.kb_total, g.kb_per_split);
+  g.C = C; g.ldc = ldc; g.c_bf16 = c_bf16; g.bias = bias;
+  g.atomic_add = (g.split_k > 1 || accumulate) ? 1 : 0;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_a(&ta, A, a_mn, lda, M, K);
+  if (rc) return rc;
+  rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn);
+  if (rc) return rc;
+#define EVC_DISPATCH(AM, BMN)                                                       \
+  if (a_mn == AM && b_mn == BMN) {                                                   \
+    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE>(ta, ta, tb, g, stream)        \
+                     : launch<AM, BMN, 128, EPI_STORE>(ta, ta, tb, g, stream);       \
+  }
+  EVC_DISPATCH(0, 0)
+  EVC_DISPATCH(0, 1)
+  EVC_DISPATCH(1, 0)
+  EVC_DISPATCH(1, 1)
+#undef EVC_DISPATCH
+  return set_error(EVC_ERR_ARG, "gemm: bad major flags");
+}
+
+}  // namespace evc
+
+using namespace evc;
+
+extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                             long long ldb, int M, int N, int K, void* C, int c_is_bf16, long long ldc,
+                             const float* bias, int split_k, int accumulate, void* stream) {
+  return gemm_store(A, a_mn_major, lda, B, b_mn_major, ldb, M, N, K, C, c_is_bf16, ldc, bias, split_k, accumulate,
+                    static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ BasicLSTM layer, forward over T steps
+extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
+                                int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
+                                void* gates_all, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: empty problem");
+  if (H % 64 != 0 || Kx % 64 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: H and Kx must be multiples of 64");
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h_all);
+  __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
+  const long long RH = static_cast<long long>(rows) * H;
+  CUtensorMap tb;
+  int rc = make_tmap_b(&tb, W, 1, 4LL * H, 4 * H, Kx + H, 256);
+  if (rc) return rc;
+  for (int t = 0; t < T; ++t) {
+    CUtensorMap ta1, ta2;
+    rc = make_tmap_a(&ta1, xb + t * x_step_stride, 0, Kx, rows, Kx);
+    if (rc) return rc;
+    rc = make_tmap_a(&ta2, hb + t * RH, 0, H, rows, H);
+    if (rc) return rc;
+    GemmArgs g = {};
+    g.M = rows; g.N = 4 * H; g.H = H;
+    g.tiles_m = ceil_div(rows, BM);
+    g.tiles_n = H / 64;
+    g.split_k = 1;
+    g.kb_a1 = Kx / BK;
+    g.kb_total = g.kb_a1 + (t == 0 ? 0 : H / BK);  // h_{-1} = 0: skip the recurrent half at t = 0
+    g.kb_per_split = g.kb_total;
+    g.bias = bias;
+    g.t = t; g.seq_len = seq_len;
+    g.c_prev = (t == 0) ? nullptr : c_all + t * RH;
+    g.h_prev = (t == 0) ? nullptr : hb + t * RH;
+    g.c_out = c_all + (t + 1) * RH;
+    g.h_out = hb + (t + 1) * RH;
+    g.gates = gb ? gb + t * RH * 4 : nullptr;
+    rc = launch<0, 1, 256, EPI_LSTM_FWD>(ta1, ta2, tb, g, stream);
+    if (rc) return rc;
+  }
+  return EVC_OK;
+}
+
+// ------------------------------------------------------------------ BasicLSTM layer, backward over T steps
+extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len,
+                                const void* gates_all, const float* c_all, const float* dh_ext_all,
+                                const float* dh_final, long long ld_dh_final, const float* dc_final,
+                                long long ld_dc_final, float* dh_pass, float* dc, void* dz_all, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: empty problem");
+  if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: H must be a multiple of 128");
+  const __nv_bfloat16* gb = static_cast<const __nv_bfloat16*>(gates_all);
+  __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(dz_all);
+  const __nv_bfloat16* wh = static_cast<const __nv_bfloat16*>(W) + static_cast<long long>(Kx) * 4 * H;
+  const long long RH = static_cast<long long>(rows) * H;
+  CUtensorMap tb;  // B[k = gate column, n = unit] = Wh[unit][gate column] : stored [N][K] = K-major
+  int rc = make_tmap_b(&tb, wh, 0, 4LL * H, H, 4 * H, 128);
+  if (rc) return rc;
+  for (int t = T - 1; t >= 0; --t) {
+    const bool last = (t == T - 1);
+    CUtensorMap ta;
+    // A = dz_{t+1} [rows, 4H]; at the last step there is no recurrent term (the map is unused)
+    rc = make_tmap_a(&ta, zb + (last ? t : t + 1) * RH * 4, 0, 4LL * H, rows, 4 * H);
+    if (rc) return rc;
+    GemmArgs g = {};
+    g.M = rows; g.N = H; g.H = H;
+    g.tiles_m = ceil_div(rows, BM);
+    g.tiles_n = H / 128;
+    g.split_k = 1;
+    g.kb_total = last ? 0 : (4 * H) / BK;
+    g.kb_a1 = g.kb_total;
+    g.kb_per_split = g.kb_total > 0 ? g.kb_total : 1;
+    g.t = t; g.seq_len = seq_len;
+    g.gates = const_cast<__nv_bfloat16*>(gb + t * RH * 4);
+    g.c_prev = (t == 0) ? nullptr : c_all + t * RH;
+    g.dh_ext = dh_ext_all ? dh_ext_all + t * RH : nullptr;
+    g.ld_dh_ext = H;
+    g.dh_pass_in = last ? dh_final : dh_pass;
+    g.ld_dh_pass_in = last ? ld_dh_final : H;
+    g.dc_in = last ? dc_final : dc;
+    g.ld_dc_in = last ? ld_dc_final : H;
+    g.dh_pass_out = dh_pass;
+    g.dc_out = dc;
+    g.dz_out = zb + t * RH * 4;
+    rc = launch<0, 0, 128, EPI_LSTM_BWD>(ta, ta, tb, g, stream);
+    if (rc) return rc;
+  }
+  return EVC_OK;
+}

@@ -1,0 +1,530 @@
+// Bandwidth-bound kernels of the H-LSTM teacher-student path (sm_100a):
+// frame normalise/gather/pack, sequence lengths, sampler index rules, state packing,
+// MoE mixture + cross-entropy, loss gradients, representation loss, bias column sums,
+// per-variable clip + TF-Adam, exact top-k.  Reference formulas are cited per kernel
+// (paths relative to /root/reference/code_student_uniform).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "evc_host.h"
+
+using namespace evc;
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {  // sh: 32 floats
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  return sh[0];
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// --------------------------------------------------------------------------------------
+// train.py:256 l2_normalize + train.py:265-272 gather (or model_utils.py:34-58 gather_nd),
+// written in the chunk-time-major bf16 layout the LSTM GEMMs read:
+//   out[(tt * C + chunk) * B + b][D]  with frame k = chunk*ell + tt  (C chunks of ell frames)
+// One warp per selected frame.
+__global__ void frames_pack_kernel(const float* __restrict__ src, int B, int T, int D,
+                                   const int* __restrict__ frame_idx, int idx_per_batch, int K, int C,
+                                   int normalize, __nv_bfloat16* __restrict__ out_bf16,
+                                   float* __restrict__ out_f32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  const int b = warp / K, k = warp % K;
+  const int f = frame_idx ? (idx_per_batch ? frame_idx[b * K + k] : frame_idx[k]) : k;
+  const float4* s = reinterpret_cast<const float4*>(src + (static_cast<long long>(b) * T + f) * D);
+  const int n4 = D >> 2;
+  float scale = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = __ldg(s + i);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    scale = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+  }
+  const int ell = K / C;
+  const int chunk = k / ell, tt = k % ell;
+  __nv_bfloat16* ob = out_bf16 ? out_bf16 + ((static_cast<long long>(tt) * C + chunk) * B + b) * D : nullptr;
+  float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + (static_cast<long long>(b) * K + k) * D) : nullptr;
+  for (int i = lane; i < n4; i += 32) {
+    float4 v = __ldg(s + i);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (ob) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(ob + 4 * i) = u;
+    }
+    if (of) of[i] = v;
+  }
+}
+
+// train.py:263-264  int64( (n / 300) * int(300/every_n) ) in float64
+__global__ void num_frames_student_kernel(const int* __restrict__ nf, int B, int max_frames, int m,
+                                          long long* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double q = static_cast<double>(nf[b]) / static_cast<double>(max_frames);
+  out[b] = static_cast<long long>(q * static_cast<double>(m));  // truncation toward zero
+}
+
+// frame_level_models.py:240,256 (teacher) / :309,327 (student)
+//   len_l1[c*B+b] = min(ell, max(0, n - ell*c));  len_l2[b] = int32(ceil(float32(n)/ell))
+__global__ void lstm_lengths_kernel(const void* __restrict__ nf, int is64, int B, int C, int ell,
+                                    int* __restrict__ len_l1, int* __restrict__ len_l2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i / B, b = i % B;
+  const long long n = is64 ? static_cast<const long long*>(nf)[b] : static_cast<const int*>(nf)[b];
+  long long v = n - static_cast<long long>(ell) * c;
+  v = v < 0 ? 0 : v;
+  v = v > ell ? ell : v;
+  len_l1[i] = static_cast<int>(v);
+  if (c == 0) len_l2[b] = static_cast<int>(ceilf(static_cast<float>(n) / static_cast<float>(ell)));
+}
+
+// model_utils.py:49-53  int32(u * float32(n))
+__global__ void random_frame_index_kernel(const float* __restrict__ u, const int* __restrict__ nf, int B, int K,
+                                          int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  idx[i] = static_cast<int>(__fmul_rn(u[i], static_cast<float>(nf[i / K])));
+}
+// model_utils.py:23-33  start = int32(u*float32(max(n-K,0)+1)); idx = min(start+k, n-1)
+__global__ void random_sequence_index_kernel(const float* __restrict__ u, const int* __restrict__ nf, int B, int K,
+                                             int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K, k = i % K;
+  const int n = nf[b];
+  const int ms = max(n - K, 0);
+  const int start = static_cast<int>(__fmul_rn(u[b], static_cast<float>(ms + 1)));
+  idx[i] = min(start + k, n - 1);
+}
+
+// MultiRNNCell(state_is_tuple=False) state = [c0|h0|c1|h1]: gather the final
+// (c, h) of both cells into the 4H-wide row that RNN_L2 / MoE / L_REP consume.
+__global__ void state_pack_kernel(const float* __restrict__ c0, const __nv_bfloat16* __restrict__ h0,
+                                  const float* __restrict__ c1, const __nv_bfloat16* __restrict__ h1, long long n,
+                                  int H, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = i / H;
+  const int u = static_cast<int>(i % H);
+  const float vc0 = c0[i], vh0 = __bfloat162float(h0[i]), vc1 = c1[i], vh1 = __bfloat162float(h1[i]);
+  const long long o = r * 4 * H + u;
+  if (out_bf16) {
+    out_bf16[o] = __float2bfloat16(vc0);
+    out_bf16[o + H] = h0[i];
+    out_bf16[o + 2 * H] = __float2bfloat16(vc1);
+    out_bf16[o + 3 * H] = h1[i];
+  }
+  if (out_f32) {
+    out_f32[o] = vc0;
+    out_f32[o + H] = vh0;
+    out_f32[o + 2 * H] = vc1;
+    out_f32[o + 3 * H] = vh1;
+  }
+}
+
+// f32 [R,C] -> bf16 [R,ld] (columns C..ld-1 zero): bf16 operand copies of weights / activations
+__global__ void cast_bf16_kernel(const float* __restrict__ src, long long R, int C, int ld,
+                                 __nv_bfloat16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= R * ld) return;
+  const long long r = i / ld;
+  const int c = static_cast<int>(i % ld);
+  dst[i] = (c < C) ? __float2bfloat16(src[r * C + c]) : __float2bfloat16(0.f);
+}
+
+// --------------------------------------------------------------------------------------
+// video_level_models.py:437-447 + losses.py:90-97.  One block per video.
+//   p[b,c] = sum_{m<M} softmax(G[b,c,0..M])[m] * sigmoid(E[b,c,m]);  CE row sum (eps = 1e-5)
+template <int MAXM>
+__device__ __forceinline__ float moe_class(const float* g, const float* e, int M, float* gate, float* sig) {
+  float mx = g[0];
+  for (int m = 1; m <= M; ++m) mx = fmaxf(mx, g[m]);
+  float den = 0.f;
+  for (int m = 0; m <= M; ++m) { gate[m] = __expf(g[m] - mx); den += gate[m]; }
+  const float inv = 1.0f / den;
+  float p = 0.f;
+  for (int m = 0; m < M; ++m) { gate[m] *= inv; sig[m] = sigmoidf_(e[m]); p += gate[m] * sig[m]; }
+  gate[M] *= inv;
+  return p;
+}
+
+__global__ void moe_mix_fwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
+                                   long long lde, int V, int M, const uint8_t* __restrict__ labels,
+                                   float* __restrict__ p_out, float* __restrict__ ce_rows) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* g = G + b * ldg;
+  const float* e = E + b * lde;
+  float ce = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float gate[9], sig[8];
+    const float p = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
+    p_out[static_cast<long long>(b) * V + c] = p;
+    if (labels) {
+      const float y = labels[static_cast<long long>(b) * V + c] ? 1.f : 0.f;
+      ce -= y * __logf(p + 1e-5f) + (1.f - y) * __logf(1.f - p + 1e-5f);
+    }
+  }
+  if (ce_rows) {
+    ce = block_sum(ce, sh);
+    if (threadIdx.x == 0) ce_rows[b] = ce;
+  }
+}
+
+// Gradient of  ce_scale * CE_row + kl_scale * KL(pT_hat || pS_hat)  w.r.t. the MoE logits
+// (losses.py:90-97; train.py:398-402 with Categorical(probs=.) renormalisation).
+//   dCE/dp = -(y/(p+eps)) + (1-y)/(1-p+eps)
+//   dKL/dp_c = -pT_hat_c / p_c + 1 / sum(pS)
+//   dG_k = g_k (s_k - p) dp  (s_M = 0 for the dummy expert),  dE_m = g_m s_m (1-s_m) dp
+__global__ void moe_loss_bwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
+                                    long long lde, const float* __restrict__ P, const float* __restrict__ PT,
+                                    const uint8_t* __restrict__ labels, int V, int M, float ce_scale,
+                                    float kl_scale, __nv_bfloat16* __restrict__ dG, long long lddg,
+                                    __nv_bfloat16* __restrict__ dE, long long ldde, float* __restrict__ kl_rows) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* g = G + b * ldg;
+  const float* e = E + b * lde;
+  const float* p = P + static_cast<long long>(b) * V;
+  const float* pt = PT ? PT + static_cast<long long>(b) * V : nullptr;
+  float inv_sT = 0.f, inv_sS = 0.f;
+  if (pt) {
+    float st = 0.f, ss = 0.f;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) { st += pt[c]; ss += p[c]; }
+    st = block_sum(st, sh);
+    ss = block_sum(ss, sh);
+    inv_sT = 1.0f / st;
+    inv_sS = 1.0f / ss;
+  }
+  float kl = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float gate[9], sig[8];
+    const float pc = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
+    const float y = labels[static_cast<long long>(b) * V + c] ? 1.f : 0.f;
+    float dp = ce_scale * (-(y / (pc + 1e-5f)) + (1.f - y) / (1.f - pc + 1e-5f));
+    if (pt) {
+      const float th = pt[c] * inv_sT;
+      dp += kl_scale * (-th / pc + inv_sS);
+      if (th > 0.f) kl += th * (__logf(th) - __logf(pc * inv_sS));
+    }
+    for (int m = 0; m <= M; ++m) {
+      const float s = (m < M) ? sig[m] : 0.f;
+      dG[b * lddg + c * (M + 1) + m] = __float2bfloat16(gate[m] * (s - pc) * dp);
+    }
+    for (int m = 0; m < M; ++m) dE[b * ldde + c * M + m] = __float2bfloat16(gate[m] * sig[m] * (1.f - sig[m]) * dp);
+  }
+  if (kl_rows) {
+    kl = block_sum(kl, sh);
+    if (threadIdx.x == 0) kl_rows[b] = kl;
+  }
+}
+
+// train.py:359-362  L_REP rows = sum_j (t - s)^2 ;  dS = grad_scale * (s - t)
+__global__ void rep_loss_kernel(const float* __restrict__ t_state, const float* __restrict__ s_state, int S,
+                                float grad_scale, float* __restrict__ rows, float* __restrict__ d_s) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const long long o = static_cast<long long>(b) * S + j;
+    const float d = s_state[o] - t_state[o];
+    acc += d * d;
+    if (d_s) d_s[o] = grad_scale * d;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) rows[b] = acc;
+}
+
+// bias gradients: out[n] += sum_r X[r, n]  (bf16 X with row pitch ld).  out must be zeroed.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long R, int N, long long ld,
+                                   long long rows_per_block, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < R) ? r0 + rows_per_block : R;
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += __bfloat162float(X[r * ld + n]);
+  atomicAdd(out + n, acc);
+}
+
+// out[0] += sum (g + wd*w)^2     (slim clip_gradient_norms: per-variable l2 norm; wd*w is the
+// gradient of penalty * l2_regularizer(1e-8)(w), video_level_models.py:428,434 / train.py:324)
+__global__ void sumsq_kernel(const float* __restrict__ g, const float* __restrict__ w, float wd, long long n,
+                             float* __restrict__ out) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float4 a = *reinterpret_cast<const float4*>(g + i);
+      if (wd != 0.f) {
+        const float4 ww = *reinterpret_cast<const float4*>(w + i);
+        a.x += wd * ww.x; a.y += wd * ww.y; a.z += wd * ww.z; a.w += wd * ww.w;
+      }
+      acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    } else {
+      for (long long j = i; j < n; ++j) {
+        const float a = g[j] + (wd != 0.f ? wd * w[j] : 0.f);
+        acc += a * a;
+      }
+    }
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// [TF clip_ops.clip_by_norm] g * c * min(rsqrt(sum g^2), 1/c), then [TF ApplyAdam]
+//   m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= lr_t * m / (sqrt(v) + eps)
+// and refresh of the bf16 operand copy of w (row pitch ld_shadow, `cols` columns per row).
+__global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, const float* __restrict__ normsq, float clip,
+                                 float wd, const float* __restrict__ lr_t, float b1, float b2, float eps,
+                                 __nv_bfloat16* __restrict__ shadow, int cols, long long ld_shadow) {
+  float scale = 1.f;
+  if (clip > 0.f) {
+    const float ns = *normsq;
+    scale = (ns > 0.f) ? clip * fminf(rsqrtf(ns), 1.0f / clip) : 1.f;
+  }
+  const float lr = *lr_t;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float wi = w[i];
+    const float gi = (g[i] + wd * wi) * scale;
+    float mi = m[i], vi = v[i];
+    mi += (gi - mi) * (1.f - b1);
+    vi += (gi * gi - vi) * (1.f - b2);
+    wi -= lr * mi / (sqrtf(vi) + eps);
+    m[i] = mi; v[i] = vi; w[i] = wi;
+    if (shadow) shadow[(i / cols) * ld_shadow + (i % cols)] = __float2bfloat16(wi);
+  }
+}
+
+// eval_util.py:118-124 top_k_triplets: the k largest predictions of a video.  Exact; the
+// reference's argpartition leaves ties at the boundary implementation-defined, here the
+// lower class index wins and the output is ordered by value descending.  One block per video.
+__global__ void topk_kernel(const float* __restrict__ P, int V, int k, const uint8_t* __restrict__ labels,
+                            int* __restrict__ idx_out, float* __restrict__ val_out, uint8_t* __restrict__ lab_out) {
+  extern __shared__ unsigned long long keys[];  // V keys + 32 scratch
+  unsigned long long* red = keys + V;
+  const int b = blockIdx.x;
+  const float* p = P + static_cast<long long>(b) * V;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    uint32_t u = __float_as_uint(p[c]);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone map float -> uint
+    keys[c] = (static_cast<unsigned long long>(u) << 32) | static_cast<uint32_t>(0xFFFFFFFFu - c);
+  }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    unsigned long long best = 0ull;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) best = keys[c] > best ? keys[c] : best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned long long v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+      }
+      if (threadIdx.x == 0) {
+        const int c = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(v & 0xFFFFFFFFull));
+        idx_out[b * k + r] = c;
+        val_out[b * k + r] = p[c];
+        if (lab_out) lab_out[b * k + r] = labels ? labels[static_cast<long long>(b) * V + c] : 0;
+        keys[c] = 0ull;  // remove from later rounds
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+inline int grid_for(long long n, int block, int cap) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+#define EVC_STREAM(s) static_cast<cudaStream_t>(s)
+
+extern "C" int evc_frames_pack(const float* src, int B, int T, int D, const int* frame_idx, int idx_per_batch,
+                               int K, int num_chunks, int normalize, void* out_bf16, float* out_f32, void* stream) {
+  if (B <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "frames_pack: empty batch");
+  if (D % 4 != 0) return set_error(EVC_ERR_ARG, "frames_pack: feature size must be a multiple of 4");
+  if (num_chunks <= 0 || K % num_chunks != 0)
+    return set_error(EVC_ERR_ARG, "frames_pack: number of frames must split evenly into chunks (tf.split)");
+  const long long warps = static_cast<long long>(B) * K;
+  const int block = 256;
+  const int grid = static_cast<int>((warps * 32 + block - 1) / block);
+  frames_pack_kernel<<<grid, block, 0, EVC_STREAM(stream)>>>(src, B, T, D, frame_idx, idx_per_batch, K, num_chunks,
+                                                             normalize, static_cast<__nv_bfloat16*>(out_bf16),
+                                                             out_f32);
+  count_launch();
+  return check_launch("frames_pack");
+}
+
+extern "C" int evc_num_frames_student(const int* num_frames, int B, int max_frames, int every_n, long long* out,
+                                      void* stream) {
+  if (every_n <= 0) return set_error(EVC_ERR_ARG, "num_frames_student: every_n must be positive");
+  num_frames_student_kernel<<<(B + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(num_frames, B, max_frames,
+                                                                             max_frames / every_n, out);
+  count_launch();
+  return check_launch("num_frames_student");
+}
+
+extern "C" int evc_lstm_lengths(const void* num_frames, int is_int64, int B, int num_chunks, int chunk_len,
+                                int* len_l1, int* len_l2, void* stream) {
+  const int n = B * num_chunks;
+  lstm_lengths_kernel<<<(n + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(num_frames, is_int64, B, num_chunks,
+                                                                       chunk_len, len_l1, len_l2);
+  count_launch();
+  return check_launch("lstm_lengths");
+}
+
+extern "C" int evc_random_frame_index(const float* u, const int* num_frames, int B, int K, int* idx, void* stream) {
+  random_frame_index_kernel<<<(B * K + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(u, num_frames, B, K, idx);
+  count_launch();
+  return check_launch("random_frame_index");
+}
+extern "C" int evc_random_sequence_index(const float* u, const int* num_frames, int B, int K, int* idx,
+                                         void* stream) {
+  random_sequence_index_kernel<<<(B * K + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(u, num_frames, B, K, idx);
+  count_launch();
+  return check_launch("random_sequence_index");
+}
+
+extern "C" int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,
+                              void* out_bf16, float* out_f32, void* stream) {
+  const long long n = static_cast<long long>(rows) * H;
+  state_pack_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, EVC_STREAM(stream)>>>(
+      c0, static_cast<const __nv_bfloat16*>(h0), c1, static_cast<const __nv_bfloat16*>(h1), n, H,
+      static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  count_launch();
+  return check_launch("state_pack");
+}
+
+extern "C" int evc_cast_bf16(const float* src, long long rows, int cols, int ld, void* dst, void* stream) {
+  if (ld < cols) return set_error(EVC_ERR_ARG, "cast_bf16: ld < cols");
+  const long long n = rows * ld;
+  cast_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, EVC_STREAM(stream)>>>(
+      src, rows, cols, ld, static_cast<__nv_bfloat16*>(dst));
+  count_launch();
+  return check_launch("cast_bf16");
+}
+
+extern "C" int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, long long lde, int B, int V, int M,
+                               const unsigned char* labels, float* p_out, float* ce_rows, void* stream) {
+  if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix: 1 <= num_mixtures <= 8");
+  moe_mix_fwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, V, M, labels, p_out, ce_rows);
+  count_launch();
+  return check_launch("moe_mix_fwd");
+}
+
+extern "C" int evc_moe_loss_bwd(const float* G, long long ldg, const float* E, long long lde, const float* P,
+                                const float* PT, const unsigned char* labels, int B, int V, int M, float ce_scale,
+                                float kl_scale, void* dG, long long lddg, void* dE, long long ldde, float* kl_rows,
+                                void* stream) {
+  if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_loss_bwd: 1 <= num_mixtures <= 8");
+  if (labels == nullptr) return set_error(EVC_ERR_ARG, "moe_loss_bwd: labels required");
+  moe_loss_bwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, P, PT, labels, V, M, ce_scale, kl_scale,
+                                                         static_cast<__nv_bfloat16*>(dG), lddg,
+                                                         static_cast<__nv_bfloat16*>(dE), ldde, kl_rows);
+  count_launch();
+  return check_launch("moe_loss_bwd");
+}
+
+extern "C" int evc_rep_loss(const float* teacher_state, const float* student_state, int B, int S, float grad_scale,
+                            float* rows, float* d_student, void* stream) {
+  rep_loss_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(teacher_state, student_state, S, grad_scale, rows, d_student);
+  count_launch();
+  return check_launch("rep_loss");
+}
+
+extern "C" int evc_colsum_bf16(const void* X, long long rows, int N, long long ld, float* out, void* stream) {
+  long long rpb = 256;
+  long long gy = (rows + rpb - 1) / rpb;
+  if (gy > 2048) { gy = 2048; rpb = (rows + gy - 1) / gy; gy = (rows + rpb - 1) / rpb; }
+  dim3 grid((N + 127) / 128, static_cast<unsigned>(gy));
+  colsum_bf16_kernel<<<grid, 128, 0, EVC_STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(X), rows, N, ld, rpb,
+                                                           out);
+  count_launch();
+  return check_launch("colsum_bf16");
+}
+
+extern "C" int evc_fill_f32(float* p, long long n, float value, void* stream) {
+  fill_f32_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(p, n, value);
+  count_launch();
+  return check_launch("fill_f32");
+}
+
+extern "C" int evc_sumsq(const float* g, const float* w, float weight_decay, long long n, float* out,
+                         void* stream) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) || (w && (reinterpret_cast<uintptr_t>(w) & 15)))
+    return set_error(EVC_ERR_ARG, "sumsq: pointers must be 16-byte aligned");
+  sumsq_kernel<<<grid_for((n + 3) / 4, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(g, w, w ? weight_decay : 0.f, n,
+                                                                                    out);
+  count_launch();
+  return check_launch("sumsq");
+}
+
+extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
+                             float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2,
+                             float eps, void* shadow_bf16, int cols, long long ld_shadow, void* stream) {
+  if (shadow_bf16 && cols <= 0) return set_error(EVC_ERR_ARG, "clip_adam: cols required with a bf16 copy");
+  clip_adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, EVC_STREAM(stream)>>>(
+      w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps,
+      static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow);
+  count_launch();
+  return check_launch("clip_adam");
+}
+
+extern "C" int evc_topk(const float* P, int B, int V, int k, const unsigned char* labels, int* idx_out,
+                        float* val_out, unsigned char* lab_out, void* stream) {
+  if (k <= 0) return set_error(EVC_ERR_ARG, "topk: k must be a positive integer");  // eval_util.py:103-104
+  if (k > V) return set_error(EVC_ERR_ARG, "topk: k > num_classes (clamp k = min(k, V) on the host)");
+  const size_t smem = (static_cast<size_t>(V) + 32) * sizeof(unsigned long long);
+  if (smem > 200 * 1024) return set_error(EVC_ERR_UNSUPPORTED, "topk: num_classes too large for one block");
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  topk_kernel<<<B, 256, smem, EVC_STREAM(stream)>>>(P, V, k, labels, idx_out, val_out, lab_out);
+  count_launch();
+  return check_launch("topk");
+}

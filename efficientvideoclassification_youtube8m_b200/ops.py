@@ -1,0 +1,150 @@
+"""Thin torch-tensor wrappers over the C ABI (include/evc.h).  Every function launches the
+hand-written sm_100a kernels on the current CUDA stream; nothing here computes on the host
+or through torch operators."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+BF16 = torch.bfloat16
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("libevc operands must be contiguous CUDA tensors")
+
+
+def pad8(n: int, mult: int = 64) -> int:
+    return (n + mult - 1) // mult * mult
+
+
+def gemm(A, B, M, N, K, out, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, bias=None,
+         split_k=1, accumulate=False):
+    """out[M,N] (=|+=) A[M,K] @ B[K,N]; see evc_gemm_bf16 for the storage conventions."""
+    lda = lda if lda is not None else A.stride(0)
+    ldb = ldb if ldb is not None else B.stride(0)
+    ldc = ldc if ldc is not None else out.stride(0)
+    check(lib.evc_gemm_bf16(ptr(A), int(a_mn), lda, ptr(B), int(b_mn), ldb, M, N, K, ptr(out),
+                            int(out.dtype == BF16), ldc, ptr(bias), split_k, int(accumulate), stream()),
+          "evc_gemm_bf16")
+    return out
+
+
+def frames_pack(src, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None):
+    _cuda(src, frame_idx, out_bf16, out_f32)
+    B, T, D = src.shape
+    per_batch = int(frame_idx is not None and frame_idx.dim() == 2)
+    check(lib.evc_frames_pack(ptr(src), B, T, D, ptr(frame_idx), per_batch, K, num_chunks, int(normalize),
+                              ptr(out_bf16), ptr(out_f32), stream()), "evc_frames_pack")
+
+
+def num_frames_student(num_frames, every_n, max_frames=300, out=None):
+    _cuda(num_frames)
+    assert num_frames.dtype == torch.int32
+    out = out if out is not None else torch.empty(num_frames.shape[0], dtype=torch.int64, device=num_frames.device)
+    check(lib.evc_num_frames_student(ptr(num_frames), num_frames.shape[0], max_frames, every_n, ptr(out), stream()),
+          "evc_num_frames_student")
+    return out
+
+
+def lstm_lengths(num_frames, num_chunks, chunk_len, len_l1=None, len_l2=None):
+    _cuda(num_frames)
+    B = num_frames.shape[0]
+    assert num_frames.dtype in (torch.int32, torch.int64)
+    dev = num_frames.device
+    len_l1 = len_l1 if len_l1 is not None else torch.empty(num_chunks * B, dtype=torch.int32, device=dev)
+    len_l2 = len_l2 if len_l2 is not None else torch.empty(B, dtype=torch.int32, device=dev)
+    check(lib.evc_lstm_lengths(ptr(num_frames), int(num_frames.dtype == torch.int64), B, num_chunks, chunk_len,
+                               ptr(len_l1), ptr(len_l2), stream()), "evc_lstm_lengths")
+    return len_l1, len_l2
+
+
+def random_frame_index(u, num_frames):
+    _cuda(u, num_frames)
+    B, K = u.shape
+    idx = torch.empty(B, K, dtype=torch.int32, device=u.device)
+    check(lib.evc_random_frame_index(ptr(u), ptr(num_frames), B, K, ptr(idx), stream()), "evc_random_frame_index")
+    return idx
+
+
+def random_sequence_index(u, num_frames, K):
+    _cuda(u, num_frames)
+    B = u.shape[0]
+    idx = torch.empty(B, K, dtype=torch.int32, device=u.device)
+    check(lib.evc_random_sequence_index(ptr(u), ptr(num_frames), B, K, ptr(idx), stream()),
+          "evc_random_sequence_index")
+    return idx
+
+
+def lstm_seq_fwd(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_all, gates_all):
+    check(lib.evc_lstm_seq_fwd(ptr(x), x_step_stride, Kx, ptr(W), ptr(bias), rows, H, T, ptr(seq_len), ptr(h_all),
+                               ptr(c_all), ptr(gates_all), stream()), "evc_lstm_seq_fwd")
+
+
+def lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates_all, c_all, dh_ext_all, dh_final, ld_dh_final, dc_final,
+                 ld_dc_final, dh_pass, dc, dz_all):
+    check(lib.evc_lstm_seq_bwd(ptr(W), Kx, rows, H, T, ptr(seq_len), ptr(gates_all), ptr(c_all), ptr(dh_ext_all),
+                               ptr(dh_final), ld_dh_final, ptr(dc_final), ld_dc_final, ptr(dh_pass), ptr(dc),
+                               ptr(dz_all), stream()), "evc_lstm_seq_bwd")
+
+
+def state_pack(c0, h0, c1, h1, rows, H, out_bf16=None, out_f32=None):
+    check(lib.evc_state_pack(ptr(c0), ptr(h0), ptr(c1), ptr(h1), rows, H, ptr(out_bf16), ptr(out_f32), stream()),
+          "evc_state_pack")
+
+
+def cast_bf16(src, dst, rows, cols, ld):
+    check(lib.evc_cast_bf16(ptr(src), rows, cols, ld, ptr(dst), stream()), "evc_cast_bf16")
+
+
+def fill_f32(t, value=0.0):
+    check(lib.evc_fill_f32(ptr(t), t.numel(), float(value), stream()), "evc_fill_f32")
+
+
+def moe_mix_fwd(G, ldg, E, lde, B, V, M, labels, p_out, ce_rows):
+    check(lib.evc_moe_mix_fwd(ptr(G), ldg, ptr(E), lde, B, V, M, ptr(labels), ptr(p_out), ptr(ce_rows), stream()),
+          "evc_moe_mix_fwd")
+
+
+def moe_loss_bwd(G, ldg, E, lde, P, PT, labels, B, V, M, ce_scale, kl_scale, dG, lddg, dE, ldde, kl_rows):
+    check(lib.evc_moe_loss_bwd(ptr(G), ldg, ptr(E), lde, ptr(P), ptr(PT), ptr(labels), B, V, M, ce_scale, kl_scale,
+                               ptr(dG), lddg, ptr(dE), ldde, ptr(kl_rows), stream()), "evc_moe_loss_bwd")
+
+
+def rep_loss(t_state, s_state, grad_scale, rows, d_student):
+    B, S = s_state.shape
+    check(lib.evc_rep_loss(ptr(t_state), ptr(s_state), B, S, grad_scale, ptr(rows), ptr(d_student), stream()),
+          "evc_rep_loss")
+
+
+def colsum_bf16(X, rows, N, ld, out):
+    check(lib.evc_colsum_bf16(ptr(X), rows, N, ld, ptr(out), stream()), "evc_colsum_bf16")
+
+
+def sumsq(g, w, weight_decay, out):
+    check(lib.evc_sumsq(ptr(g), ptr(w), weight_decay, g.numel(), ptr(out), stream()), "evc_sumsq")
+
+
+def clip_adam(w, g, m, v, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps, shadow=None, cols=0,
+              ld_shadow=0):
+    check(lib.evc_clip_adam(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(normsq), clip_norm, weight_decay,
+                            ptr(lr_t), beta1, beta2, eps, ptr(shadow), cols, ld_shadow, stream()), "evc_clip_adam")
+
+
+def topk(P, k, labels=None):
+    """eval_util.top_k_triplets on the device: (idx int32 [B,k], val f32 [B,k], lab u8 [B,k] | None)."""
+    _cuda(P, labels)
+    if k <= 0:
+        raise ValueError("k must be a positive integer.")  # eval_util.py:103-104
+    B, V = P.shape
+    k = min(k, V)
+    idx = torch.empty(B, k, dtype=torch.int32, device=P.device)
+    val = torch.empty(B, k, dtype=torch.float32, device=P.device)
+    lab = torch.empty(B, k, dtype=torch.uint8, device=P.device) if labels is not None else None
+    if B > 0:
+        check(lib.evc_topk(ptr(P), B, V, k, ptr(labels), ptr(idx), ptr(val), ptr(lab), stream()), "evc_topk")
+    return idx, val, lab

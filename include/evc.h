@@ -1,0 +1,136 @@
+/*
+ * libevc -- C ABI of the B200-native (sm_100a) Hierarchical-LSTM teacher-student hot path
+ * of shwetabhardwaj44/EfficientVideoClassification_Youtube8M.
+ *
+ * The reference is a pure-Python TensorFlow-1.x graph: it has no FFI of its own (SURVEY.md
+ * 2.1), so each entry point below cites the reference op chain (file:line, relative to
+ * /root/reference/code_student_uniform) whose arithmetic it replaces.  The Python plugin
+ * classes in efficientvideoclassification_youtube8m_b200/ bind these with ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, performs
+ *     no allocation and no host synchronisation (so sequences of calls are CUDA-graph capturable)
+ *   - return value: 0 = ok, <0 = EVC_ERR_*; text via evc_last_error() (thread local)
+ *   - "bf16" buffers are __nv_bfloat16 (passed as void*); TMA operands must be 16-byte aligned
+ *     with a row pitch that is a multiple of 8 elements
+ *   - lstm weight `W` is the BasicLSTMCell kernel [in+H, 4H] (rows = [x ; h], gate column order
+ *     i, j, f, o) exactly as TF lays it out, converted to bf16
+ */
+#ifndef EVC_H_
+#define EVC_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVC_OK 0
+#define EVC_ERR_ARG (-1)
+#define EVC_ERR_CUDA (-2)
+#define EVC_ERR_UNSUPPORTED (-3)
+
+int evc_version(void);
+const char* evc_last_error(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+long long evc_launch_count(void);
+
+/* ---- input: tf.nn.l2_normalize (train.py:256) + uniform gather (train.py:265-272) or
+ * gather_nd of sampled frames (model_utils.py:34-36,55-58), fused with the split into
+ * num_chunks sub-sequences (frame_level_models.py:237,307).
+ * src f32 [B,T,D]; frame_idx int32 [K] (idx_per_batch=0), [B,K] (=1) or NULL (identity, K<=T).
+ * out_bf16 (nullable): [(tt*num_chunks + chunk)*B + b][D], frame k = chunk*(K/num_chunks)+tt.
+ * out_f32 (nullable): [B,K,D] (the tensor the reference feeds to create_model*). */
+int evc_frames_pack(const float* src, int B, int T, int D, const int* frame_idx, int idx_per_batch, int K,
+                    int num_chunks, int normalize, void* out_bf16, float* out_f32, void* stream);
+
+/* train.py:263-264: int64((num_frames / 300) * int(300/every_n)), evaluated in float64. */
+int evc_num_frames_student(const int* num_frames, int B, int max_frames, int every_n, long long* out,
+                           void* stream);
+
+/* frame_level_models.py:240,256 / :309,327: len_l1[c*B+b] = min(l, max(0, n - l*c)),
+ * len_l2[b] = int32(ceil(float32(n)/l)).  num_frames is int32 (is_int64=0) or int64 (=1). */
+int evc_lstm_lengths(const void* num_frames, int is_int64, int B, int num_chunks, int chunk_len, int* len_l1,
+                     int* len_l2, void* stream);
+
+/* model_utils.py:49-53 SampleRandomFrames index rule: idx[b,k] = int32(u[b,k]*float32(n_b)). */
+int evc_random_frame_index(const float* u, const int* num_frames, int B, int K, int* idx, void* stream);
+/* model_utils.py:23-33 SampleRandomSequence: start=int32(u[b]*float32(max(n-K,0)+1)); min(start+k,n-1). */
+int evc_random_sequence_index(const float* u, const int* num_frames, int B, int K, int* idx, void* stream);
+
+/* ---- dense contraction on tcgen05 tensor cores: C[M,N] (=|+=) A[M,K] * B[K,N] (+ bias[N]).
+ * a_mn_major=0: A stored [M][lda] (K contiguous); 1: stored [K][lda] (M contiguous).
+ * b_mn_major=0: B stored [N][ldb] (K contiguous); 1: stored [K][ldb] (N contiguous).
+ * C f32 or bf16 with row pitch ldc.  split_k>1 or accumulate!=0 adds into C with f32 atomics
+ * (C must then be f32 and pre-initialised).  Replaces TF MatMul inside BasicLSTMCell._linear
+ * and slim.fully_connected (video_level_models.py:423-435) and their gradients. */
+int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
+                  int M, int N, int K, void* C, int c_is_bf16, long long ldc, const float* bias, int split_k,
+                  int accumulate, void* stream);
+
+/* ---- tf.nn.dynamic_rnn(BasicLSTMCell(H, forget_bias=1.0), x, sequence_length) for ONE cell of
+ * the MultiRNNCell stack (frame_level_models.py:221-257, 291-328), all `rows` sequences at once.
+ * Per step one fused kernel: [x_t | h_{t-1}] * W on tcgen05, then in the epilogue bias, gate
+ * non-linearities, c/h update and the `t >= sequence_length` state copy-through.
+ * x bf16: step t at x + t*x_step_stride, [rows,Kx].  h_all bf16 [(T+1),rows,H] and c_all f32
+ * [(T+1),rows,H] receive the state after every step (slot 0 = initial zero state, not read).
+ * gates_all bf16 [T,rows,4H] (nullable) keeps the post-activation gates for the backward pass. */
+int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias, int rows,
+                     int H, int T, const int* seq_len, void* h_all, float* c_all, void* gates_all, void* stream);
+
+/* Backward twin: for t = T-1..0 one fused kernel computing dz_{t+1} * Wh^T on tcgen05 and, in the
+ * epilogue, the gate gradients dz_t (bf16 [T,rows,4H]) with the sequence_length mask.
+ * dh_ext_all f32 [T,rows,H] (nullable): gradient w.r.t. the cell output at each step (from the cell
+ * above).  dh_final/dc_final (nullable, row pitches ld_*): gradient w.r.t. the final state.
+ * dh_pass, dc: f32 [rows,H] scratch. */
+int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len, const void* gates_all,
+                     const float* c_all, const float* dh_ext_all, const float* dh_final, long long ld_dh_final,
+                     const float* dc_final, long long ld_dc_final, float* dh_pass, float* dc, void* dz_all,
+                     void* stream);
+
+/* final MultiRNNCell state [c0|h0|c1|h1] (state_is_tuple=False; frame_level_models.py:252,257). */
+int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,
+                   void* out_bf16, float* out_f32, void* stream);
+
+/* f32 [rows,cols] -> bf16 [rows,ld] operand copy (pad columns zeroed). */
+int evc_cast_bf16(const float* src, long long rows, int cols, int ld, void* dst, void* stream);
+int evc_fill_f32(float* p, long long n, float value, void* stream);
+
+/* ---- MoeModel mixture (video_level_models.py:437-447) + CrossEntropyLoss (losses.py:90-97).
+ * G f32 [B,ldg] gate logits (column c*(M+1)+m), E f32 [B,lde] expert logits (c*M+m, bias added).
+ * p_out f32 [B,V]; ce_rows f32 [B] (nullable, needs labels u8 [B,V]). */
+int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, long long lde, int B, int V, int M,
+                    const unsigned char* labels, float* p_out, float* ce_rows, void* stream);
+
+/* d(ce_scale*CE_row + kl_scale*KL(pT||pS)) / d logits  (losses.py:90-97, train.py:398-402).
+ * PT nullable (no L_PRED term).  dG/dE bf16 with row pitches lddg/ldde; kl_rows f32 [B] nullable. */
+int evc_moe_loss_bwd(const float* G, long long ldg, const float* E, long long lde, const float* P,
+                     const float* PT, const unsigned char* labels, int B, int V, int M, float ce_scale,
+                     float kl_scale, void* dG, long long lddg, void* dE, long long ldde, float* kl_rows,
+                     void* stream);
+
+/* L_REP (train.py:359-362): rows[b] = sum_j (t-s)^2; d_student (nullable) = grad_scale*(s-t). */
+int evc_rep_loss(const float* teacher_state, const float* student_state, int B, int S, float grad_scale,
+                 float* rows, float* d_student, void* stream);
+
+/* out[n] += sum_r X[r,n] (bias gradients; out pre-zeroed). */
+int evc_colsum_bf16(const void* X, long long rows, int N, long long ld, float* out, void* stream);
+
+/* ---- slim.learning.create_train_op (train.py:329-334,413-418): per-variable clip_by_norm + Adam.
+ * evc_sumsq: out[0] += sum (g + weight_decay*w)^2 (w nullable).
+ * evc_clip_adam: g' = (g + wd*w) * c*min(rsqrt(normsq),1/c) (clip_norm<=0: no clip); TF ApplyAdam
+ * with lr_t read from device memory; refreshes the bf16 operand copy (nullable). */
+int evc_sumsq(const float* g, const float* w, float weight_decay, long long n, float* out, void* stream);
+int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
+                  float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2, float eps,
+                  void* shadow_bf16, int cols, long long ld_shadow, void* stream);
+
+/* ---- eval_util.py:118-124 top_k_triplets: per video the k largest predictions (value desc,
+ * lower class index first among equals), their values and (nullable) labels. */
+int evc_topk(const float* P, int B, int V, int k, const unsigned char* labels, int* idx_out, float* val_out,
+             unsigned char* lab_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVC_H_ */

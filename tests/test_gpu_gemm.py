@@ -1,0 +1,118 @@
+"""tcgen05 GEMM family against torch (bf16-rounded operands, f32/f64 accumulation)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(shape, generator=g).to(torch.bfloat16).cuda()
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (300, 200, 136), (512, 1024, 1152),
+                                   (96, 4716 * 3, 320)])
+def test_gemm_all_majors(a_mn, b_mn, M, N, K):
+    from efficientvideoclassification_youtube8m_b200 import ops
+    Mp, Np, Kp = ops.pad8(M, 8), ops.pad8(N, 8), ops.pad8(K, 8)
+    # storage with padded pitches (TMA needs 16-byte multiples)
+    A = _mk((K, Mp), 1) if a_mn else _mk((M, Kp), 1)
+    B = _mk((K, Np), 2) if b_mn else _mk((N, Kp), 2)
+    Al = (A[:, :M].t() if a_mn else A[:, :K]).double()
+    Bl = (B[:, :N] if b_mn else B[:, :K].t()).double()
+    ref = Al @ Bl
+    bias = torch.randn(N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, bias=bias)
+    torch.cuda.synchronize()
+    err = (out.double() - (ref + bias.double())).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_bf16_out_and_splitk():
+    from efficientvideoclassification_youtube8m_b200 import ops
+    M, N, K = 256, 512, 4096
+    A, B = _mk((M, K), 3), _mk((N, K), 4)
+    ref = A.double() @ B.double().t()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, B, M, N, K, out)
+    assert (out.double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+    acc = torch.ones(M, N, device="cuda")
+    ops.gemm(A, B, M, N, K, acc, split_k=8)
+    torch.cuda.synchronize()
+    assert (acc.double() - 1 - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+def _lstm_ref(x, W, b, seq_len, T, H, dtype=torch.float64):
+    """dynamic_rnn(BasicLSTMCell) with autograd, x [T,rows,Kx]."""
+    rows = x.shape[1]
+    c = torch.zeros(rows, H, dtype=dtype, device=x.device)
+    h = torch.zeros(rows, H, dtype=dtype, device=x.device)
+    hs = []
+    for t in range(T):
+        z = torch.cat([x[t], h], 1) @ W + b
+        i, j, f, o = z.chunk(4, 1)
+        cn = c * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
+        hn = torch.tanh(cn) * torch.sigmoid(o)
+        live = (t < seq_len).unsqueeze(1)
+        c = torch.where(live, cn, c)
+        h = torch.where(live, hn, h)
+        hs.append(hn)
+    return c, h, torch.stack(hs)
+
+
+@pytest.mark.parametrize("rows,Kx,H,T", [(200, 128, 128, 5), (256, 1152, 1024, 3)])
+def test_lstm_seq_fwd_bwd(rows, Kx, H, T):
+    from efficientvideoclassification_youtube8m_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = (torch.randn(T, rows, Kx, device=dev) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)).to(torch.bfloat16)
+    b = torch.randn(4 * H, device=dev) * 0.1
+    seq_len = torch.randint(0, T + 1, (rows,), device=dev, dtype=torch.int32)
+    seq_len[:4] = torch.tensor([0, 1, T, T - 1], dtype=torch.int32)
+    h_all = torch.zeros(T + 1, rows, H, dtype=torch.bfloat16, device=dev)
+    c_all = torch.zeros(T + 1, rows, H, device=dev)
+    gates = torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev)
+    ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates)
+    torch.cuda.synchronize()
+
+    xd = x.double().requires_grad_(True)
+    Wd = W.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    c_ref, h_ref, hs_ref = _lstm_ref(xd, Wd, bd, seq_len, T, H)
+    assert (c_all[T].double() - c_ref).abs().max().item() < 2e-2
+    assert (h_all[T].double() - h_ref).abs().max().item() < 2e-2
+
+    # backward: loss = sum(dc_f*c_T) + sum(dh_f*h_T) + sum(dh_ext * h_new_t)
+    dc_f = torch.randn(rows, H, device=dev)
+    dh_f = torch.randn(rows, H, device=dev)
+    dh_ext = torch.randn(T, rows, H, device=dev) * 0.5
+    live_all = (torch.arange(T, device=dev).view(T, 1) < seq_len.view(1, rows)).unsqueeze(2)
+    loss = (dc_f.double() * c_ref).sum() + (dh_f.double() * h_ref).sum() + \
+        (torch.where(live_all, dh_ext.double(), torch.zeros_like(dh_ext.double())) * hs_ref).sum()
+    gx, gW, gb = torch.autograd.grad(loss, [xd, Wd, bd])
+
+    dz = torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev)
+    dh_pass = torch.zeros(rows, H, device=dev)
+    dc = torch.zeros(rows, H, device=dev)
+    dh_ext_masked = torch.where(live_all, dh_ext, torch.zeros_like(dh_ext)).contiguous()
+    ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc, dz)
+    # wgrad: dW = [x | h_prev]^T dz ; dX = dz Wx^T ; db = colsum dz
+    dW = torch.zeros(Kx + H, 4 * H, device=dev)
+    R = T * rows
+    ops.gemm(x.view(R, Kx), dz.view(R, 4 * H), Kx, 4 * H, R, dW[:Kx], a_mn=True, b_mn=True, ldc=4 * H)
+    ops.gemm(h_all.view((T + 1) * rows, H), dz.view(R, 4 * H), H, 4 * H, R, dW[Kx:], a_mn=True, b_mn=True, ldc=4 * H)
+    dX = torch.zeros(R, Kx, device=dev)
+    ops.gemm(dz.view(R, 4 * H), W, R, Kx, 4 * H, dX)
+    db = torch.zeros(4 * H, device=dev)
+    ops.colsum_bf16(dz, R, 4 * H, 4 * H, db)
+    torch.cuda.synchronize()
+
+    def rel(a, bref):
+        return ((a.double() - bref).norm() / (bref.norm() + 1e-30)).item()
+    assert rel(dW, gW) < 3e-2, rel(dW, gW)
+    assert rel(dX.view(T, rows, Kx), gx) < 3e-2, rel(dX.view(T, rows, Kx), gx)
+    assert rel(db, gb) < 3e-2, rel(db, gb)
