@@ -26,11 +26,14 @@ SIGNATURES = {
     "evc_state_pack": [P, P, P, P, I, I, P, P, P],
     "evc_cast_bf16": [P, L, I, I, P, P],
     "evc_fill_f32": [P, L, F, P],
-    "evc_moe_mix_fwd": [P, L, P, L, I, I, I, P, P, P, P],
-    "evc_moe_loss_bwd": [P, L, P, L, P, P, P, I, I, I, F, F, P, L, P, L, P, P],
+    "evc_moe_mix_fwd": [P, L, P, L, I, I, I, P, P],
+    "evc_moe_mix_bwd": [P, L, P, L, P, I, I, I, P, L, P, L, P],
+    "evc_ce_kl_loss": [P, P, P, I, I, F, F, P, P, P, P],
+    "evc_reduce_rows": [P, I, F, P, P],
+    "evc_adam_lr": [P, F, F, F, P, P],
     "evc_rep_loss": [P, P, I, I, F, P, P, P],
     "evc_colsum_bf16": [P, L, I, L, P, P],
-    "evc_sumsq": [P, P, F, L, P, P],
+    "evc_sumsq": [P, P, F, L, P, P, P],
     "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P],
     "evc_topk": [P, I, I, I, P, P, P, P, P],
 }

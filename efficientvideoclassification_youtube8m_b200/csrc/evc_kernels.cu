@@ -172,44 +172,50 @@ __device__ __forceinline__ float moe_class(const float* g, const float* e, int M
 }
 
 __global__ void moe_mix_fwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
-                                   long long lde, int V, int M, const uint8_t* __restrict__ labels,
-                                   float* __restrict__ p_out, float* __restrict__ ce_rows) {
-  __shared__ float sh[32];
+                                   long long lde, int V, int M, float* __restrict__ p_out) {
   const int b = blockIdx.x;
   const float* g = G + b * ldg;
   const float* e = E + b * lde;
-  float ce = 0.f;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
     float gate[9], sig[8];
-    const float p = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
-    p_out[static_cast<long long>(b) * V + c] = p;
-    if (labels) {
-      const float y = labels[static_cast<long long>(b) * V + c] ? 1.f : 0.f;
-      ce -= y * __logf(p + 1e-5f) + (1.f - y) * __logf(1.f - p + 1e-5f);
-    }
-  }
-  if (ce_rows) {
-    ce = block_sum(ce, sh);
-    if (threadIdx.x == 0) ce_rows[b] = ce;
+    p_out[static_cast<long long>(b) * V + c] = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
   }
 }
 
-// Gradient of  ce_scale * CE_row + kl_scale * KL(pT_hat || pS_hat)  w.r.t. the MoE logits
-// (losses.py:90-97; train.py:398-402 with Categorical(probs=.) renormalisation).
-//   dCE/dp = -(y/(p+eps)) + (1-y)/(1-p+eps)
-//   dKL/dp_c = -pT_hat_c / p_c + 1 / sum(pS)
-//   dG_k = g_k (s_k - p) dp  (s_M = 0 for the dummy expert),  dE_m = g_m s_m (1-s_m) dp
-__global__ void moe_loss_bwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
-                                    long long lde, const float* __restrict__ P, const float* __restrict__ PT,
-                                    const uint8_t* __restrict__ labels, int V, int M, float ce_scale,
-                                    float kl_scale, __nv_bfloat16* __restrict__ dG, long long lddg,
-                                    __nv_bfloat16* __restrict__ dE, long long ldde, float* __restrict__ kl_rows) {
-  __shared__ float sh[32];
+// Backward of the mixture: dG_k = g_k (s_k - p) dp  (s_M = 0 for the dummy expert),
+//                          dE_m = g_m s_m (1 - s_m) dp        (bf16 outputs = GEMM operands)
+__global__ void moe_mix_bwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
+                                   long long lde, const float* __restrict__ dP, int V, int M,
+                                   __nv_bfloat16* __restrict__ dG, long long lddg, __nv_bfloat16* __restrict__ dE,
+                                   long long ldde) {
   const int b = blockIdx.x;
   const float* g = G + b * ldg;
   const float* e = E + b * lde;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float gate[9], sig[8];
+    const float pc = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
+    const float dp = dP[static_cast<long long>(b) * V + c];
+    for (int m = 0; m <= M; ++m) {
+      const float s = (m < M) ? sig[m] : 0.f;
+      dG[b * lddg + c * (M + 1) + m] = __float2bfloat16(gate[m] * (s - pc) * dp);
+    }
+    for (int m = 0; m < M; ++m) dE[b * ldde + c * M + m] = __float2bfloat16(gate[m] * sig[m] * (1.f - sig[m]) * dp);
+  }
+}
+
+// losses.py:90-97 CrossEntropyLoss rows and train.py:398-402 KL(Categorical(probs=pT) ||
+// Categorical(probs=pS)) rows (both are renormalised), plus the gradient of
+//   ce_scale * CE_row + kl_scale * KL_row   w.r.t. the student predictions:
+//   dCE/dp = -(y/(p+eps)) + (1-y)/(1-p+eps) ;  dKL/dp_c = -pT_hat_c / p_c + 1 / sum(pS)
+__global__ void ce_kl_loss_kernel(const float* __restrict__ P, const float* __restrict__ PT,
+                                  const uint8_t* __restrict__ labels, int V, float ce_scale, float kl_scale,
+                                  float* __restrict__ ce_rows, float* __restrict__ kl_rows,
+                                  float* __restrict__ dP) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
   const float* p = P + static_cast<long long>(b) * V;
   const float* pt = PT ? PT + static_cast<long long>(b) * V : nullptr;
+  const uint8_t* y8 = labels ? labels + static_cast<long long>(b) * V : nullptr;
   float inv_sT = 0.f, inv_sS = 0.f;
   if (pt) {
     float st = 0.f, ss = 0.f;
@@ -219,27 +225,49 @@ __global__ void moe_loss_bwd_kernel(const float* __restrict__ G, long long ldg, 
     inv_sT = 1.0f / st;
     inv_sS = 1.0f / ss;
   }
-  float kl = 0.f;
+  float kl = 0.f, ce = 0.f;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    float gate[9], sig[8];
-    const float pc = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
-    const float y = labels[static_cast<long long>(b) * V + c] ? 1.f : 0.f;
-    float dp = ce_scale * (-(y / (pc + 1e-5f)) + (1.f - y) / (1.f - pc + 1e-5f));
+    const float pc = p[c];
+    float dp = 0.f;
+    if (y8) {
+      const float y = y8[c] ? 1.f : 0.f;
+      ce -= y * __logf(pc + 1e-5f) + (1.f - y) * __logf(1.f - pc + 1e-5f);
+      dp += ce_scale * (-(y / (pc + 1e-5f)) + (1.f - y) / (1.f - pc + 1e-5f));
+    }
     if (pt) {
       const float th = pt[c] * inv_sT;
       dp += kl_scale * (-th / pc + inv_sS);
       if (th > 0.f) kl += th * (__logf(th) - __logf(pc * inv_sS));
     }
-    for (int m = 0; m <= M; ++m) {
-      const float s = (m < M) ? sig[m] : 0.f;
-      dG[b * lddg + c * (M + 1) + m] = __float2bfloat16(gate[m] * (s - pc) * dp);
-    }
-    for (int m = 0; m < M; ++m) dE[b * ldde + c * M + m] = __float2bfloat16(gate[m] * sig[m] * (1.f - sig[m]) * dp);
+    if (dP) dP[static_cast<long long>(b) * V + c] = dp;
+  }
+  if (ce_rows) {
+    ce = block_sum(ce, sh);
+    if (threadIdx.x == 0) ce_rows[b] = ce;
   }
   if (kl_rows) {
     kl = block_sum(kl, sh);
     if (threadIdx.x == 0) kl_rows[b] = kl;
   }
+}
+
+// out[0] = scale * sum_i rows[i]  (reduce_mean / reduce_sum over the batch); single block
+__global__ void reduce_rows_kernel(const float* __restrict__ rows, int n, float scale, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += rows[i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = acc * scale;
+}
+
+// [TF adam.py _prepare/_finish] t += 1 ; lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
+__global__ void adam_lr_kernel(long long* __restrict__ step, float lr, float b1, float b2,
+                               float* __restrict__ lr_t) {
+  const long long t = step[0] + 1;
+  step[0] = t;
+  const double td = static_cast<double>(t);
+  lr_t[0] = static_cast<float>(static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(b2), td)) /
+                               (1.0 - pow(static_cast<double>(b1), td)));
 }
 
 // train.py:359-362  L_REP rows = sum_j (t - s)^2 ;  dS = grad_scale * (s - t)
@@ -273,27 +301,33 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long lon
 // out[0] += sum (g + wd*w)^2     (slim clip_gradient_norms: per-variable l2 norm; wd*w is the
 // gradient of penalty * l2_regularizer(1e-8)(w), video_level_models.py:428,434 / train.py:324)
 __global__ void sumsq_kernel(const float* __restrict__ g, const float* __restrict__ w, float wd, long long n,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, float* __restrict__ out_wsq) {
   __shared__ float sh[32];
-  float acc = 0.f;
+  float acc = 0.f, wacc = 0.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
       float4 a = *reinterpret_cast<const float4*>(g + i);
-      if (wd != 0.f) {
+      if (w != nullptr) {
         const float4 ww = *reinterpret_cast<const float4*>(w + i);
         a.x += wd * ww.x; a.y += wd * ww.y; a.z += wd * ww.z; a.w += wd * ww.w;
+        wacc += ww.x * ww.x + ww.y * ww.y + ww.z * ww.z + ww.w * ww.w;
       }
       acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
     } else {
       for (long long j = i; j < n; ++j) {
-        const float a = g[j] + (wd != 0.f ? wd * w[j] : 0.f);
+        const float a = g[j] + (w != nullptr ? wd * w[j] : 0.f);
         acc += a * a;
+        if (w != nullptr) wacc += w[j] * w[j];
       }
     }
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (out_wsq != nullptr) {
+    wacc = block_sum(wacc, sh);
+    if (threadIdx.x == 0) atomicAdd(out_wsq, wacc);
+  }
 }
 
 // [TF clip_ops.clip_by_norm] g * c * min(rsqrt(sum g^2), 1/c), then [TF ApplyAdam]
@@ -448,24 +482,44 @@ extern "C" int evc_cast_bf16(const float* src, long long rows, int cols, int ld,
 }
 
 extern "C" int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, long long lde, int B, int V, int M,
-                               const unsigned char* labels, float* p_out, float* ce_rows, void* stream) {
+                               float* p_out, void* stream) {
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix: 1 <= num_mixtures <= 8");
-  moe_mix_fwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, V, M, labels, p_out, ce_rows);
+  if (B <= 0) return EVC_OK;
+  moe_mix_fwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, V, M, p_out);
   count_launch();
   return check_launch("moe_mix_fwd");
 }
 
-extern "C" int evc_moe_loss_bwd(const float* G, long long ldg, const float* E, long long lde, const float* P,
-                                const float* PT, const unsigned char* labels, int B, int V, int M, float ce_scale,
-                                float kl_scale, void* dG, long long lddg, void* dE, long long ldde, float* kl_rows,
-                                void* stream) {
-  if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_loss_bwd: 1 <= num_mixtures <= 8");
-  if (labels == nullptr) return set_error(EVC_ERR_ARG, "moe_loss_bwd: labels required");
-  moe_loss_bwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, P, PT, labels, V, M, ce_scale, kl_scale,
-                                                         static_cast<__nv_bfloat16*>(dG), lddg,
-                                                         static_cast<__nv_bfloat16*>(dE), ldde, kl_rows);
+extern "C" int evc_moe_mix_bwd(const float* G, long long ldg, const float* E, long long lde, const float* dP, int B,
+                               int V, int M, void* dG, long long lddg, void* dE, long long ldde, void* stream) {
+  if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix_bwd: 1 <= num_mixtures <= 8");
+  if (B <= 0) return EVC_OK;
+  moe_mix_bwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, dP, V, M, static_cast<__nv_bfloat16*>(dG),
+                                                        lddg, static_cast<__nv_bfloat16*>(dE), ldde);
   count_launch();
-  return check_launch("moe_loss_bwd");
+  return check_launch("moe_mix_bwd");
+}
+
+extern "C" int evc_ce_kl_loss(const float* P, const float* PT, const unsigned char* labels, int B, int V,
+                              float ce_scale, float kl_scale, float* ce_rows, float* kl_rows, float* dP,
+                              void* stream) {
+  if (labels == nullptr && PT == nullptr) return set_error(EVC_ERR_ARG, "ce_kl_loss: labels or teacher needed");
+  if (B <= 0) return EVC_OK;
+  ce_kl_loss_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(P, PT, labels, V, ce_scale, kl_scale, ce_rows, kl_rows, dP);
+  count_launch();
+  return check_launch("ce_kl_loss");
+}
+
+extern "C" int evc_reduce_rows(const float* rows, int n, float scale, float* out, void* stream) {
+  reduce_rows_kernel<<<1, 256, 0, EVC_STREAM(stream)>>>(rows, n, scale, out);
+  count_launch();
+  return check_launch("reduce_rows");
+}
+
+extern "C" int evc_adam_lr(long long* step, float lr, float beta1, float beta2, float* lr_t, void* stream) {
+  adam_lr_kernel<<<1, 1, 0, EVC_STREAM(stream)>>>(step, lr, beta1, beta2, lr_t);
+  count_launch();
+  return check_launch("adam_lr");
 }
 
 extern "C" int evc_rep_loss(const float* teacher_state, const float* student_state, int B, int S, float grad_scale,
@@ -493,11 +547,11 @@ extern "C" int evc_fill_f32(float* p, long long n, float value, void* stream) {
 }
 
 extern "C" int evc_sumsq(const float* g, const float* w, float weight_decay, long long n, float* out,
-                         void* stream) {
+                         float* out_wsq, void* stream) {
   if ((reinterpret_cast<uintptr_t>(g) & 15) || (w && (reinterpret_cast<uintptr_t>(w) & 15)))
     return set_error(EVC_ERR_ARG, "sumsq: pointers must be 16-byte aligned");
   sumsq_kernel<<<grid_for((n + 3) / 4, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(g, w, w ? weight_decay : 0.f, n,
-                                                                                    out);
+                                                                                    out, w ? out_wsq : nullptr);
   count_launch();
   return check_launch("sumsq");
 }

@@ -1,0 +1,183 @@
+"""Execution plan of one Hierarchical-LSTM model instance on one B200.
+
+Restates frame_level_models.py:200-338 (HierarchicalLstmModel.create_model /
+create_model_inference) + video_level_models.py:397-448 (MoeModel) as a fixed sequence of
+libevc kernel launches over pre-allocated HBM buffers:
+
+  frames_pack -> [RNN_L1 cell0, cell1 over all chunks as one batch] -> state_pack
+              -> [RNN_L2 cell0, cell1] -> state_pack -> gates/experts GEMMs -> mixture
+
+The `num_chunks` lower-level dynamic_rnn calls of the reference share weights and start
+from a zero state, so they run as one batch of num_chunks*B rows.  The two
+cells of a MultiRNNCell are evaluated layer by layer (cell 1 reads the whole h-sequence
+of cell 0), which lets every time step be one fused GEMM+cell kernel.
+
+Memory layout (all row-major, per model instance, B = batch, C = chunks, l = frames/chunk,
+R1 = C*B rows at the lower level):
+  x      bf16 [l][R1][D]          row = chunk*B + b      (time-major inside a chunk)
+  h_all  bf16 [T+1][rows][H]      c_all f32 [T+1][rows][H]   gates bf16 [T][rows][4H]
+  l2_in  bf16 [C][B][4H]          = final [c0|h0|c1|h1] of every chunk (RNN_L2 input)
+  state  f32  [B][4H]             final MultiRNNCell state of RNN_L2 (MoE input, L_REP operand)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .params import HLstmParams
+
+BF16 = torch.bfloat16
+
+
+class _Layer:
+    """Buffers of one BasicLSTMCell unrolled over T steps for `rows` sequences."""
+
+    def __init__(self, rows, H, T, training, dev):
+        self.rows, self.H, self.T = rows, H, T
+        self.h_all = torch.zeros(T + 1, rows, H, dtype=BF16, device=dev)
+        self.c_all = torch.zeros(T + 1, rows, H, dtype=torch.float32, device=dev)
+        self.gates = torch.empty(T, rows, 4 * H, dtype=BF16, device=dev) if training else None
+        self.dz = torch.empty(T, rows, 4 * H, dtype=BF16, device=dev) if training else None
+
+
+class HLstmEngine:
+    def __init__(self, params: HLstmParams, batch: int, num_frames_in: int, num_chunks: int,
+                 training: bool = True):
+        cfg = params.cfg
+        if num_frames_in % num_chunks != 0:
+            raise ValueError("tf.split: number of frames must be divisible by the number of chunks")
+        self.p, self.cfg = params, cfg
+        self.B, self.K, self.C = batch, num_frames_in, num_chunks
+        self.ell = num_frames_in // num_chunks
+        self.training = training
+        dev = params.device
+        H, D, V, M, S = cfg.lstm_cells, cfg.feature_size, cfg.vocab_size, cfg.num_mixtures, cfg.state_size
+        self.R1 = self.C * self.B
+        B, R1, ell, C = self.B, self.R1, self.ell, self.C
+        self.x = torch.empty(ell, R1, D, dtype=BF16, device=dev)
+        self.len_l1 = torch.zeros(R1, dtype=torch.int32, device=dev)
+        self.len_l2 = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.l1 = [_Layer(R1, H, ell, training, dev) for _ in range(2)]
+        self.l2_in = torch.empty(C, B, S, dtype=BF16, device=dev)
+        self.l2 = [_Layer(B, H, C, training, dev) for _ in range(2)]
+        self.state = torch.empty(B, S, dtype=torch.float32, device=dev)
+        self.state_bf16 = torch.empty(B, S, dtype=BF16, device=dev)
+        self.ldg, self.lde = V * (M + 1), V * M
+        self.G = torch.empty(B, self.ldg, dtype=torch.float32, device=dev)
+        self.E = torch.empty(B, self.lde, dtype=torch.float32, device=dev)
+        self.pred = torch.empty(B, V, dtype=torch.float32, device=dev)
+        if training:
+            self.lddg, self.ldde = ops.pad8(self.ldg, 64), ops.pad8(self.lde, 64)
+            self.dG = torch.zeros(B, self.lddg, dtype=BF16, device=dev)
+            self.dE = torch.zeros(B, self.ldde, dtype=BF16, device=dev)
+            self.dP = torch.empty(B, V, dtype=torch.float32, device=dev)
+            self.dstate = torch.zeros(B, S, dtype=torch.float32, device=dev)
+            self.dx_l2 = torch.empty(C * B, H, dtype=torch.float32, device=dev)       # d h0 sequence of RNN_L2
+            self.dl2_in = torch.empty(R1, S, dtype=torch.float32, device=dev)         # d final state of every chunk
+            self.dx_l1 = torch.empty(ell * R1, H, dtype=torch.float32, device=dev)    # d h0 sequence of RNN_L1
+            self.scr_l1 = (torch.empty(R1, H, dtype=torch.float32, device=dev),
+                           torch.empty(R1, H, dtype=torch.float32, device=dev))
+            self.scr_l2 = (torch.empty(B, H, dtype=torch.float32, device=dev),
+                           torch.empty(B, H, dtype=torch.float32, device=dev))
+
+    # ------------------------------------------------------------------ forward
+    def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len):
+        p = self.p
+        ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
+                         layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates)
+
+    def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
+                num_frames: torch.Tensor) -> None:
+        """src f32 [B, T_src, D]; frame_idx int32 [K] / [B,K] / None; num_frames int32|int64 [B]
+        (already the *sampled* count for the student).  Fills self.state and self.pred."""
+        cfg = self.cfg
+        H, D, S = cfg.lstm_cells, cfg.feature_size, cfg.state_size
+        B, R1, ell, C = self.B, self.R1, self.ell, self.C
+        if src.shape[0] != B or src.shape[2] != D:
+            raise ValueError(f"model_input shape {tuple(src.shape)} does not match the plan [{B},*,{D}]")
+        ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x)
+        ops.lstm_lengths(num_frames, C, ell, self.len_l1, self.len_l2)
+        a, b = self.l1
+        self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1)
+        self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1)
+        ops.state_pack(a.c_all[ell], a.h_all[ell], b.c_all[ell], b.h_all[ell], R1, H, out_bf16=self.l2_in)
+        a2, b2 = self.l2
+        self._cell_fwd(a2, self.l2_in, B * S, S, 1, 0, self.len_l2)
+        self._cell_fwd(b2, a2.h_all[1:], B * H, H, 1, 1, self.len_l2)
+        ops.state_pack(a2.c_all[C], a2.h_all[C], b2.c_all[C], b2.h_all[C], B, H,
+                       out_bf16=self.state_bf16, out_f32=self.state)
+        self.classifier_forward()
+
+    def classifier_forward(self) -> None:
+        """MoeModel on self.state_bf16 -> self.pred (video_level_models.py:423-447)."""
+        p, cfg = self.p, self.cfg
+        S, V, M = cfg.state_size, cfg.vocab_size, cfg.num_mixtures
+        ops.gemm(self.state_bf16, p.shadow[p.gates_w], self.B, self.ldg, S, self.G, b_mn=True)
+        ops.gemm(self.state_bf16, p.shadow[p.experts_w], self.B, self.lde, S, self.E, b_mn=True,
+                 bias=p.w[p.experts_b])
+        ops.moe_mix_fwd(self.G, self.ldg, self.E, self.lde, self.B, V, M, self.pred)
+
+    # ------------------------------------------------------------------ backward
+    def _cell_bwd(self, layer: _Layer, level, cell, Kx, seq_len, dh_ext, dfinal, col, scratch):
+        """dfinal: f32 [rows, 4H] gradient of the final [c0|h0|c1|h1]; this cell owns columns
+        [col, col+H) (c) and [col+H, col+2H) (h)."""
+        p = self.p
+        H = layer.H
+        ld = dfinal.stride(0)
+        ops.lstm_seq_bwd(p.shadow[p.kernel(level, cell)], Kx, layer.rows, H, layer.T, seq_len, layer.gates,
+                         layer.c_all, dh_ext, dfinal[:, col + H:], ld, dfinal[:, col:], ld,
+                         scratch[0], scratch[1], layer.dz)
+
+    def _cell_wgrad(self, layer: _Layer, level, cell, x2d, Kx):
+        """dW = [x | h_prev]^T dz over all steps and rows; db = column sums of dz."""
+        p = self.p
+        H, R = layer.H, layer.T * layer.rows
+        dz = layer.dz.view(R, 4 * H)
+        gW = p.g[p.kernel(level, cell)]
+        ops.gemm(x2d, dz, Kx, 4 * H, R, gW[:Kx], a_mn=True, b_mn=True, lda=Kx, ldc=4 * H)
+        ops.gemm(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], a_mn=True, b_mn=True, lda=H, ldc=4 * H)
+        gb = p.g[p.bias(level, cell)]
+        ops.fill_f32(gb, 0.0)
+        ops.colsum_bf16(dz, R, 4 * H, 4 * H, gb)
+
+    def _cell_dx(self, layer: _Layer, level, cell, Kx, out):
+        """d input sequence = dz @ Wx^T  (Wx = first Kx rows of the kernel)."""
+        p = self.p
+        H, R = layer.H, layer.T * layer.rows
+        ops.gemm(layer.dz.view(R, 4 * H), p.shadow[p.kernel(level, cell)], R, Kx, 4 * H, out, ldb=4 * H)
+
+    def backward(self, dP: torch.Tensor, dstate_preset: bool = False) -> None:
+        """Gradients of every weight into params.g given dP = dLoss/dpredictions [B,V].
+        If dstate_preset, self.dstate already holds dLoss/dstate from other consumers of the
+        state (L_REP) and the classifier's contribution is added to it."""
+        p, cfg = self.p, self.cfg
+        H, D, S, V, M = cfg.lstm_cells, cfg.feature_size, cfg.state_size, cfg.vocab_size, cfg.num_mixtures
+        B, R1, ell, C = self.B, self.R1, self.ell, self.C
+        # ---- classifier
+        ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde)
+        if not dstate_preset:
+            ops.fill_f32(self.dstate, 0.0)
+        ops.gemm(self.dG, p.shadow[p.gates_w], B, S, self.ldg, self.dstate, split_k=8, accumulate=True)
+        ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=8, accumulate=True)
+        ops.gemm(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], a_mn=True, b_mn=True)
+        ops.gemm(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], a_mn=True, b_mn=True)
+        gbe = p.g[p.experts_b]
+        ops.fill_f32(gbe, 0.0)
+        ops.colsum_bf16(self.dE, B, self.lde, self.ldde, gbe)
+        # ---- RNN_L2 (cell 1 first: its input gradient feeds cell 0)
+        a2, b2 = self.l2
+        self._cell_bwd(b2, 1, 1, H, self.len_l2, None, self.dstate, 2 * H, self.scr_l2)
+        self._cell_wgrad(b2, 1, 1, a2.h_all[1:].view(-1, H), H)
+        self._cell_dx(b2, 1, 1, H, self.dx_l2)
+        self._cell_bwd(a2, 1, 0, S, self.len_l2, self.dx_l2, self.dstate, 0, self.scr_l2)
+        self._cell_wgrad(a2, 1, 0, self.l2_in.view(-1, S), S)
+        self._cell_dx(a2, 1, 0, S, self.dl2_in)
+        # ---- RNN_L1: final-state gradient of chunk i = gradient of RNN_L2's input at step i
+        a, b = self.l1
+        self._cell_bwd(b, 0, 1, H, self.len_l1, None, self.dl2_in, 2 * H, self.scr_l1)
+        self._cell_wgrad(b, 0, 1, a.h_all[1:].view(-1, H), H)
+        self._cell_dx(b, 0, 1, H, self.dx_l1)
+        self._cell_bwd(a, 0, 0, D, self.len_l1, self.dx_l1, self.dl2_in, 0, self.scr_l1)
+        self._cell_wgrad(a, 0, 0, self.x.view(-1, D), D)

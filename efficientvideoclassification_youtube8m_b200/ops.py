@@ -105,14 +105,27 @@ def fill_f32(t, value=0.0):
     check(lib.evc_fill_f32(ptr(t), t.numel(), float(value), stream()), "evc_fill_f32")
 
 
-def moe_mix_fwd(G, ldg, E, lde, B, V, M, labels, p_out, ce_rows):
-    check(lib.evc_moe_mix_fwd(ptr(G), ldg, ptr(E), lde, B, V, M, ptr(labels), ptr(p_out), ptr(ce_rows), stream()),
-          "evc_moe_mix_fwd")
+def moe_mix_fwd(G, ldg, E, lde, B, V, M, p_out):
+    check(lib.evc_moe_mix_fwd(ptr(G), ldg, ptr(E), lde, B, V, M, ptr(p_out), stream()), "evc_moe_mix_fwd")
 
 
-def moe_loss_bwd(G, ldg, E, lde, P, PT, labels, B, V, M, ce_scale, kl_scale, dG, lddg, dE, ldde, kl_rows):
-    check(lib.evc_moe_loss_bwd(ptr(G), ldg, ptr(E), lde, ptr(P), ptr(PT), ptr(labels), B, V, M, ce_scale, kl_scale,
-                               ptr(dG), lddg, ptr(dE), ldde, ptr(kl_rows), stream()), "evc_moe_loss_bwd")
+def moe_mix_bwd(G, ldg, E, lde, dP, B, V, M, dG, lddg, dE, ldde):
+    check(lib.evc_moe_mix_bwd(ptr(G), ldg, ptr(E), lde, ptr(dP), B, V, M, ptr(dG), lddg, ptr(dE), ldde, stream()),
+          "evc_moe_mix_bwd")
+
+
+def ce_kl_loss(P, PT, labels, ce_scale, kl_scale, ce_rows, kl_rows, dP):
+    B, V = P.shape
+    check(lib.evc_ce_kl_loss(ptr(P), ptr(PT), ptr(labels), B, V, ce_scale, kl_scale, ptr(ce_rows), ptr(kl_rows),
+                             ptr(dP), stream()), "evc_ce_kl_loss")
+
+
+def reduce_rows(rows, scale, out):
+    check(lib.evc_reduce_rows(ptr(rows), rows.numel(), scale, ptr(out), stream()), "evc_reduce_rows")
+
+
+def adam_lr(step, lr, beta1, beta2, lr_t):
+    check(lib.evc_adam_lr(ptr(step), lr, beta1, beta2, ptr(lr_t), stream()), "evc_adam_lr")
 
 
 def rep_loss(t_state, s_state, grad_scale, rows, d_student):
@@ -125,8 +138,8 @@ def colsum_bf16(X, rows, N, ld, out):
     check(lib.evc_colsum_bf16(ptr(X), rows, N, ld, ptr(out), stream()), "evc_colsum_bf16")
 
 
-def sumsq(g, w, weight_decay, out):
-    check(lib.evc_sumsq(ptr(g), ptr(w), weight_decay, g.numel(), ptr(out), stream()), "evc_sumsq")
+def sumsq(g, w, weight_decay, out, out_wsq=None):
+    check(lib.evc_sumsq(ptr(g), ptr(w), weight_decay, g.numel(), ptr(out), ptr(out_wsq), stream()), "evc_sumsq")
 
 
 def clip_adam(w, g, m, v, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps, shadow=None, cols=0,

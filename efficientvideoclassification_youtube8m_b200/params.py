@@ -1,0 +1,176 @@
+"""The 11-tensor weight layout of one H-LSTM model (README.md:98,105; validate.py:350-374;
+train_convert_model.py:501-511) held in HBM:
+
+  * one flat f32 buffer each for the master weights, gradients and the two Adam moments
+    (so the data-parallel allreduce and the optimizer stream over contiguous memory);
+  * per-tensor views keyed by the exact TF variable names (``state_dict`` round-trips a
+    reference checkpoint's name->array map);
+  * bf16 operand copies of the five matrices in the SAME [rows, cols] orientation TF uses
+    (row pitch padded to 64 elements for TMA), refreshed by the fused clip+Adam kernel.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclass(frozen=True)
+class ModelConfig:
+    feature_size: int = 1152      # rgb 1024 + audio 128 (run_train.sh --feature_sizes "1024, 128")
+    lstm_cells: int = 1024        # FLAGS.lstm_cells
+    lstm_layers: int = 2          # run_train.sh --lstm_layers 2
+    vocab_size: int = 4716        # reader.num_classes
+    num_mixtures: int = 2         # FLAGS.moe_num_mixtures
+    l2_penalty: float = 1e-8      # MoeModel.create_model default (video_level_models.py:401)
+
+    @property
+    def state_size(self) -> int:
+        return 2 * self.lstm_layers * self.lstm_cells
+
+
+def variable_names(scope: str) -> List[str]:
+    names = []
+    for level in ("RNN_L1", "RNN_L2"):
+        for cell in (0, 1):
+            base = f"{scope}/{level}/rnn/multi_rnn_cell/cell_{cell}/basic_lstm_cell"
+            names += [base + "/kernel", base + "/bias"]
+    names += [f"{scope}/classifier/gates/weights", f"{scope}/classifier/experts/weights",
+              f"{scope}/classifier/experts/biases"]
+    return names
+
+
+def variable_shapes(scope: str, cfg: ModelConfig) -> Dict[str, tuple]:
+    if cfg.lstm_layers != 2:
+        raise NotImplementedError("the hot path is the 2-layer stack of run_train.sh (--lstm_layers 2)")
+    H, S, D, V, M = cfg.lstm_cells, cfg.state_size, cfg.feature_size, cfg.vocab_size, cfg.num_mixtures
+    n = variable_names(scope)
+    return {n[0]: (D + H, 4 * H), n[1]: (4 * H,), n[2]: (2 * H, 4 * H), n[3]: (4 * H,),
+            n[4]: (S + H, 4 * H), n[5]: (4 * H,), n[6]: (2 * H, 4 * H), n[7]: (4 * H,),
+            n[8]: (S, V * (M + 1)), n[9]: (S, V * M), n[10]: (V * M,)}
+
+
+class HLstmParams:
+    """Weights, gradients, Adam state and bf16 operand copies of one variable scope."""
+
+    def __init__(self, scope: str, cfg: ModelConfig, device, seed: Optional[int] = 0,
+                 lstm_gain: float = 1.0):
+        self.scope, self.cfg, self.device = scope, cfg, torch.device(device)
+        self.names = variable_names(scope)
+        self.shapes = variable_shapes(scope, cfg)
+        self.offsets, off = {}, 0
+        for n in self.names:
+            self.offsets[n] = off
+            numel = int(np.prod(self.shapes[n]))
+            assert numel % 4 == 0, "tensor sizes must keep 16-byte alignment inside the flat buffer"
+            off += numel
+        self.numel = off
+        self.flat_w = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.flat_m = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.flat_v = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.w, self.g, self.m, self.v = {}, {}, {}, {}
+        for n in self.names:
+            o, shp = self.offsets[n], self.shapes[n]
+            k = int(np.prod(shp))
+            self.w[n] = self.flat_w[o:o + k].view(shp)
+            self.g[n] = self.flat_g[o:o + k].view(shp)
+            self.m[n] = self.flat_m[o:o + k].view(shp)
+            self.v[n] = self.flat_v[o:o + k].view(shp)
+        # bf16 operand copies (matrices only), row pitch padded to a multiple of 64
+        self.shadow, self.ld = {}, {}
+        for n in self.names:
+            shp = self.shapes[n]
+            if len(shp) == 2:
+                ld = ops.pad8(shp[1], 64)
+                self.ld[n] = ld
+                self.shadow[n] = torch.zeros(shp[0], ld, dtype=torch.bfloat16, device=self.device)
+        self.normsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
+        self.wsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if seed is not None:
+            self.init_glorot(seed, lstm_gain)
+
+    # ---- names of the individual tensors
+    def kernel(self, level: int, cell: int) -> str:
+        return self.names[(level * 2 + cell) * 2]
+
+    def bias(self, level: int, cell: int) -> str:
+        return self.names[(level * 2 + cell) * 2 + 1]
+
+    @property
+    def gates_w(self) -> str:
+        return self.names[8]
+
+    @property
+    def experts_w(self) -> str:
+        return self.names[9]
+
+    @property
+    def experts_b(self) -> str:
+        return self.names[10]
+
+    # ---- initialisation / checkpoint interchange
+    def init_glorot(self, seed: int, lstm_gain: float = 1.0) -> None:
+        """TF defaults: glorot_uniform kernels / xavier fully_connected weights, zero biases
+        (SURVEY Appendix A.6).  Same RandomState stream as oracle.init_params."""
+        rng = np.random.RandomState(seed)
+        sd = {}
+        for n in self.names:
+            shp = self.shapes[n]
+            if len(shp) == 1:
+                sd[n] = np.zeros(shp, dtype=np.float32)
+            else:
+                limit = math.sqrt(6.0 / (shp[0] + shp[1]))
+                w = rng.uniform(-limit, limit, size=shp)
+                if "basic_lstm_cell" in n:
+                    w = w * lstm_gain
+                sd[n] = w.astype(np.float32)
+        self.load_state_dict(sd)
+
+    def load_state_dict(self, sd: Dict[str, "np.ndarray | torch.Tensor"], strict: bool = True) -> None:
+        missing = [n for n in self.names if n not in sd]
+        if missing and strict:
+            raise KeyError(f"missing variables: {missing}")
+        for n in self.names:
+            if n not in sd:
+                continue
+            t = torch.as_tensor(np.asarray(sd[n]) if not torch.is_tensor(sd[n]) else sd[n])
+            if tuple(t.shape) != tuple(self.shapes[n]):
+                raise ValueError(f"{n}: shape {tuple(t.shape)} != {self.shapes[n]}")
+            self.w[n].copy_(t.to(torch.float32))
+        self.refresh_shadows()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {n: self.w[n].detach().clone() for n in self.names}
+
+    def refresh_shadows(self) -> None:
+        for n, s in self.shadow.items():
+            rows, cols = self.shapes[n]
+            ops.cast_bf16(self.w[n], s, rows, cols, self.ld[n])
+
+    # ---- slim.learning.create_train_op: per-variable clip_by_norm + Adam (train.py:329-334)
+    def apply_gradients(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
+                        beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
+        """g <- g + penalty*l2_penalty*w for the two MoE matrices (gradient of
+        penalty * slim.l2_regularizer(l2_penalty)(w)), per-variable clip, TF Adam, bf16 refresh."""
+        wd = float(regularization_penalty) * self.cfg.l2_penalty
+        ops.fill_f32(self.normsq, 0.0)
+        ops.fill_f32(self.wsq, 0.0)
+        ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
+        reg = (self.gates_w, self.experts_w)
+        for i, n in enumerate(self.names):
+            w = self.w[n] if n in reg else None
+            ops.sumsq(self.g[n], w, wd, self.normsq[i:i + 1], self.wsq[i:i + 1] if w is not None else None)
+        for i, n in enumerate(self.names):
+            shadow = self.shadow.get(n)
+            cols = self.shapes[n][1] if shadow is not None else 0
+            ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],
+                          float(clip_gradient_norm), wd if n in reg else 0.0, self.lr_t, beta1, beta2, eps,
+                          shadow, cols, self.ld.get(n, 0))

@@ -1,0 +1,226 @@
+"""Step functions: what the reference's ``build_graph`` + one ``sess.run`` do, as fixed launch
+sequences over two :class:`HLstmEngine` plans.
+
+  TeacherStudentTrainer.step   <- train.py:185-427 build_graph + train.py:516 sess.run
+  StudentFinetuneTrainer.step  <- train_finetune.py:185-331 + :404
+  TeacherStudentEvaluator      <- validate.py:109-189 (student predictions inside the T+S graph)
+  StudentEvaluator             <- eval_finetune.py:108-175
+
+Inputs are the raw (dequantised, un-normalised) frame features ``model_input_raw`` f32
+[B,300,D], ``num_frames`` int32 [B] and ``labels`` bool/uint8 [B,V] on the device — what the
+reference's reader queue hands to the graph.  Data parallelism: every rank runs the
+same step on its own batch; gradients are averaged with one NCCL allreduce per model over the
+flat gradient buffer before the per-variable clip + Adam.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import HLstmEngine
+from .params import HLstmParams, ModelConfig
+
+MAX_FRAMES = 300  # train.py:262
+
+
+def uniform_frame_indices(every_n: int):
+    """train.py:265-269."""
+    out, k = [], 0
+    while every_n * k <= MAX_FRAMES - 1:
+        out.append(every_n * k)
+        k += 1
+    return out
+
+
+def _as_u8(labels: torch.Tensor) -> torch.Tensor:
+    if labels.dtype == torch.uint8:
+        return labels
+    if labels.dtype == torch.bool:
+        return labels.view(torch.uint8)
+    raise TypeError("labels must be a bool or uint8 tensor [B, vocab_size]")
+
+
+class _Base:
+    def __init__(self, cfg: ModelConfig, batch_size: int, device, every_n: int, num_inputs_L1: int,
+                 base_learning_rate: float, clip_gradient_norm: float, regularization_penalty: float):
+        self.cfg, self.B, self.device = cfg, batch_size, torch.device(device)
+        self.every_n, self.num_inputs_L1 = every_n, num_inputs_L1
+        self.lr, self.clip, self.penalty = base_learning_rate, clip_gradient_norm, regularization_penalty
+        idx = uniform_frame_indices(every_n)
+        if len(idx) % num_inputs_L1 != 0:
+            raise ValueError(f"every_n={every_n}: {len(idx)} sampled frames do not split into "
+                             f"{num_inputs_L1} chunks (tf.split would fail, SURVEY F13)")
+        self.student_frames = len(idx)
+        self.frame_idx = torch.tensor(idx, dtype=torch.int32, device=self.device)
+        self.nf_student = torch.zeros(batch_size, dtype=torch.int64, device=self.device)
+        self.global_step = 0
+        self._graph = None
+
+    @staticmethod
+    def _world():
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _allreduce(self, params: HLstmParams):
+        if self._world() > 1:
+            dist.all_reduce(params.flat_g, op=dist.ReduceOp.AVG)
+
+    def _check(self, raw, num_frames, labels):
+        if raw.dtype != torch.float32 or raw.dim() != 3 or raw.shape[1] != MAX_FRAMES:
+            raise ValueError("model_input_raw must be f32 [B, 300, feature_size]")
+        if num_frames.dtype != torch.int32:
+            raise TypeError("num_frames must be int32 (readers.py: tf.minimum(..., max_frames))")
+        if labels is not None and tuple(labels.shape) != (raw.shape[0], self.cfg.vocab_size):
+            raise ValueError("labels must be [B, vocab_size]")
+
+
+class TeacherStudentTrainer(_Base):
+    """Joint teacher+student training step (run_train.sh)."""
+
+    def __init__(self, cfg: ModelConfig = ModelConfig(), batch_size: int = 256, device="cuda",
+                 every_n: int = 10, num_inputs_to_lstm: int = 20, num_inputs_L1: int = 5,
+                 base_learning_rate: float = 1e-3, clip_gradient_norm: float = 1.0,
+                 regularization_penalty: float = 2.0, teacher_seed: Optional[int] = 0,
+                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0):
+        super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
+                         clip_gradient_norm, regularization_penalty)
+        self.teacher = HLstmParams("model", cfg, device, teacher_seed, lstm_gain)
+        self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
+        self.t_eng = HLstmEngine(self.teacher, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=True)
+        self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
+        dev, B = self.device, batch_size
+        self.rows = torch.zeros(4, B, dtype=torch.float32, device=dev)   # CE_T, CE_S, KL, REP rows
+        self.losses = torch.zeros(8, dtype=torch.float32, device=dev)    # CE_T, CE_S, L_PRED, L_REP
+
+    def forward_backward(self, raw, num_frames, labels_u8):
+        B = self.B
+        t, s = self.t_eng, self.s_eng
+        # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
+        t.forward(raw, None, True, num_frames)
+        # student: every_n-th frame, float64 length rule (train.py:262-272,349-357)
+        ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
+        s.forward(raw, self.frame_idx, True, self.nf_student)
+        # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term
+        ops.ce_kl_loss(t.pred, None, labels_u8, 1.0 / B, 0.0, self.rows[0], None, t.dP)
+        t.backward(t.dP)
+        # student loss = 2*L_REP + L_PRED + L_CE + penalty*reg (train.py:359-406); teacher tensors are
+        # constants for the student's backward (F9)
+        ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
+        ops.ce_kl_loss(s.pred, t.pred, labels_u8, 1.0 / B, 1.0, self.rows[1], self.rows[2], s.dP)
+        s.backward(s.dP, dstate_preset=True)
+        ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
+        ops.reduce_rows(self.rows[1], 1.0 / B, self.losses[1:2])
+        ops.reduce_rows(self.rows[2], 1.0, self.losses[2:3])
+        ops.reduce_rows(self.rows[3], 1.0 / B, self.losses[3:4])
+
+    def apply_gradients(self):
+        self.teacher.apply_gradients(self.lr, self.clip, self.penalty)
+        self.student.apply_gradients(self.lr, self.clip, self.penalty)
+
+    def step(self, model_input_raw, num_frames, labels) -> None:
+        """One iteration = both train ops (global_step += 2).  Asynchronous; read
+        results with :meth:`fetch`."""
+        self._check(model_input_raw, num_frames, labels)
+        self.forward_backward(model_input_raw, num_frames, _as_u8(labels))
+        self._allreduce(self.teacher)
+        self._allreduce(self.student)
+        self.apply_gradients()
+        self.global_step += 2
+
+    def fetch(self) -> Dict[str, float]:
+        """Device->host read of the step's scalars (the reference fetches them in sess.run and
+        checks the loss with check_numerics)."""
+        v = self.losses.tolist()
+        wsq_t = self.teacher.wsq.tolist()
+        wsq_s = self.student.wsq.tolist()
+        reg_t = self.cfg.l2_penalty * 0.5 * (wsq_t[8] + wsq_t[9])
+        reg_s = self.cfg.l2_penalty * 0.5 * (wsq_s[8] + wsq_s[9])
+        out = {"teacher_ce": v[0], "teacher_reg": reg_t, "teacher_loss": self.penalty * reg_t + v[0],
+               "l_ce": v[1], "l_pred": v[2], "l_rep": v[3], "student_reg": reg_s,
+               "student_loss": 2 * v[3] + v[2] + v[1] + self.penalty * reg_s, "global_step": self.global_step}
+        for k in ("teacher_loss", "student_loss"):
+            if out[k] != out[k] or out[k] in (float("inf"), float("-inf")):
+                raise FloatingPointError("LossTensor is inf or nan")   # slim create_train_op check_numerics
+        return out
+
+
+class StudentFinetuneTrainer(_Base):
+    """Student-only fine-tuning step (run_finetune.sh; final_loss = penalty*reg + L_CE)."""
+
+    def __init__(self, cfg: ModelConfig = ModelConfig(), batch_size: int = 256, device="cuda",
+                 every_n: int = 10, num_inputs_L1: int = 5, base_learning_rate: float = 1e-3,
+                 clip_gradient_norm: float = 1.0, regularization_penalty: float = 2.0,
+                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0):
+        super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
+                         clip_gradient_norm, regularization_penalty)
+        self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
+        self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
+        self.rows = torch.zeros(1, batch_size, dtype=torch.float32, device=self.device)
+        self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)
+
+    def step(self, model_input_raw, num_frames, labels) -> None:
+        self._check(model_input_raw, num_frames, labels)
+        B, s = self.B, self.s_eng
+        ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
+        s.forward(model_input_raw, self.frame_idx, True, self.nf_student)
+        ops.ce_kl_loss(s.pred, None, _as_u8(labels), 1.0 / B, 0.0, self.rows[0], None, s.dP)
+        s.backward(s.dP)
+        ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
+        self._allreduce(self.student)
+        self.student.apply_gradients(self.lr, self.clip, self.penalty)
+        self.global_step += 1
+
+    def fetch(self) -> Dict[str, float]:
+        v = self.losses.tolist()
+        wsq = self.student.wsq.tolist()
+        reg = self.cfg.l2_penalty * 0.5 * (wsq[8] + wsq[9])
+        out = {"l_ce": v[0], "student_reg": reg, "student_loss": self.penalty * reg + v[0],
+               "global_step": self.global_step}
+        if out["student_loss"] != out["student_loss"]:
+            raise FloatingPointError("LossTensor is inf or nan")
+        return out
+
+
+class StudentEvaluator(_Base):
+    """Student-only inference + top-k (eval_finetune.py:108-175, run_eval.sh)."""
+
+    def __init__(self, params: HLstmParams, batch_size: int, every_n: int = 10, num_inputs_L1: int = 5,
+                 top_k: int = 20):
+        super().__init__(params.cfg, batch_size, params.device, every_n, num_inputs_L1, 0.0, 0.0, 0.0)
+        self.student = params
+        self.s_eng = HLstmEngine(params, batch_size, self.student_frames, num_inputs_L1, training=False)
+        self.top_k = top_k
+        self.rows = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
+
+    def step(self, model_input_raw, num_frames, labels=None):
+        """Returns (predictions [B,V], top-k idx, top-k values, top-k labels|None); CE rows in self.rows."""
+        self._check(model_input_raw, num_frames, labels)
+        s = self.s_eng
+        ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
+        s.forward(model_input_raw, self.frame_idx, True, self.nf_student)
+        lab = _as_u8(labels) if labels is not None else None
+        if lab is not None:
+            ops.ce_kl_loss(s.pred, None, lab, 1.0, 0.0, self.rows, None, None)
+        idx, val, tl = ops.topk(s.pred, self.top_k, lab)
+        return s.pred, idx, val, tl
+
+
+class TeacherEvaluator(_Base):
+    """Teacher (all 300 frames) inference + top-k: the other half of validate.py:149-155 and the
+    denominator of the student/teacher inference-cost ratio (BASELINE config #2)."""
+
+    def __init__(self, params: HLstmParams, batch_size: int, num_inputs_to_lstm: int = 20, top_k: int = 20):
+        super().__init__(params.cfg, batch_size, params.device, 10, 5, 0.0, 0.0, 0.0)
+        self.teacher = params
+        self.t_eng = HLstmEngine(params, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=False)
+        self.top_k = top_k
+
+    def step(self, model_input_raw, num_frames, labels=None):
+        self._check(model_input_raw, num_frames, labels)
+        t = self.t_eng
+        t.forward(model_input_raw, None, True, num_frames)
+        lab = _as_u8(labels) if labels is not None else None
+        idx, val, tl = ops.topk(t.pred, self.top_k, lab)
+        return t.pred, idx, val, tl

@@ -96,18 +96,23 @@ int evc_state_pack(const float* c0, const void* h0, const float* c1, const void*
 int evc_cast_bf16(const float* src, long long rows, int cols, int ld, void* dst, void* stream);
 int evc_fill_f32(float* p, long long n, float value, void* stream);
 
-/* ---- MoeModel mixture (video_level_models.py:437-447) + CrossEntropyLoss (losses.py:90-97).
+/* ---- MoeModel mixture (video_level_models.py:437-447).
  * G f32 [B,ldg] gate logits (column c*(M+1)+m), E f32 [B,lde] expert logits (c*M+m, bias added).
- * p_out f32 [B,V]; ce_rows f32 [B] (nullable, needs labels u8 [B,V]). */
+ * p_out f32 [B,V] = sum_{m<M} softmax(G[b,c,:])[m] * sigmoid(E[b,c,m]). */
 int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, long long lde, int B, int V, int M,
-                    const unsigned char* labels, float* p_out, float* ce_rows, void* stream);
+                    float* p_out, void* stream);
+/* its backward: dP f32 [B,V] -> dG, dE (bf16 GEMM operands with row pitches lddg / ldde). */
+int evc_moe_mix_bwd(const float* G, long long ldg, const float* E, long long lde, const float* dP, int B, int V,
+                    int M, void* dG, long long lddg, void* dE, long long ldde, void* stream);
 
-/* d(ce_scale*CE_row + kl_scale*KL(pT||pS)) / d logits  (losses.py:90-97, train.py:398-402).
- * PT nullable (no L_PRED term).  dG/dE bf16 with row pitches lddg/ldde; kl_rows f32 [B] nullable. */
-int evc_moe_loss_bwd(const float* G, long long ldg, const float* E, long long lde, const float* P,
-                     const float* PT, const unsigned char* labels, int B, int V, int M, float ce_scale,
-                     float kl_scale, void* dG, long long lddg, void* dE, long long ldde, float* kl_rows,
-                     void* stream);
+/* CrossEntropyLoss rows (losses.py:90-97, eps=1e-5; labels u8 [B,V], nullable) and L_PRED rows
+ * KL(Categorical(probs=PT) || Categorical(probs=P)) (train.py:398-402; PT nullable), and
+ * dP (nullable) = d(ce_scale*CE_row + kl_scale*KL_row)/dP. */
+int evc_ce_kl_loss(const float* P, const float* PT, const unsigned char* labels, int B, int V, float ce_scale,
+                   float kl_scale, float* ce_rows, float* kl_rows, float* dP, void* stream);
+
+/* out[0] = scale * sum rows[0..n)  (tf.reduce_mean / reduce_sum over the batch). */
+int evc_reduce_rows(const float* rows, int n, float scale, float* out, void* stream);
 
 /* L_REP (train.py:359-362): rows[b] = sum_j (t-s)^2; d_student (nullable) = grad_scale*(s-t). */
 int evc_rep_loss(const float* teacher_state, const float* student_state, int B, int S, float grad_scale,
@@ -117,10 +122,13 @@ int evc_rep_loss(const float* teacher_state, const float* student_state, int B, 
 int evc_colsum_bf16(const void* X, long long rows, int N, long long ld, float* out, void* stream);
 
 /* ---- slim.learning.create_train_op (train.py:329-334,413-418): per-variable clip_by_norm + Adam.
- * evc_sumsq: out[0] += sum (g + weight_decay*w)^2 (w nullable).
+ * evc_sumsq: out[0] += sum (g + weight_decay*w)^2 and out_wsq[0] += sum w^2 (w, out_wsq nullable).
  * evc_clip_adam: g' = (g + wd*w) * c*min(rsqrt(normsq),1/c) (clip_norm<=0: no clip); TF ApplyAdam
  * with lr_t read from device memory; refreshes the bf16 operand copy (nullable). */
-int evc_sumsq(const float* g, const float* w, float weight_decay, long long n, float* out, void* stream);
+int evc_sumsq(const float* g, const float* w, float weight_decay, long long n, float* out, float* out_wsq,
+              void* stream);
+/* [TF adam.py] step[0] += 1; lr_t[0] = lr*sqrt(1-beta2^t)/(1-beta1^t) (device-resident step counter). */
+int evc_adam_lr(long long* step, float lr, float beta1, float beta2, float* lr_t, void* stream);
 int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
                   float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2, float eps,
                   void* shadow_bf16, int cols, long long ld_shadow, void* stream);

@@ -1,0 +1,114 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs and weights.  Tolerances: indices / lengths / top-k exact; predictions 1e-3 abs
+(north_star: FP32-accumulate with BF16 GEMM operands); losses 1 %; gradients 3 % (l2, relative)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(feature_size=128, lstm_cells=128, vocab_size=200, num_mixtures=2)
+
+
+def _oracle_params(O, scope, seed, cfgkw, gain):
+    return O.init_params(scope, seed, dtype=torch.float64, gain=gain, **cfgkw)
+
+
+def _setup(cfgkw, B, gain, seed=7, stress=False):
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import TeacherStudentTrainer
+    cfg = ModelConfig(**cfgkw)
+    x, nf, lab = O.synthetic_batch(B, seed=seed, num_features=cfg.feature_size, vocab_size=cfg.vocab_size,
+                                   stress=stress)
+    tr = TeacherStudentTrainer(cfg, batch_size=B, device="cuda", lstm_gain=gain)
+    T = _oracle_params(O, "model", 0, cfgkw, gain)
+    S = _oracle_params(O, "model_student", 1, cfgkw, gain)
+    # identical f32 weights on both sides
+    for n in tr.teacher.names:
+        assert torch.equal(tr.teacher.w[n].cpu().double(), T[n].float().double())
+    return O, cfg, tr, (x, nf, lab), T, S
+
+
+# gain scales the LSTM kernels: 1.0 is the reference's own initial distribution (all gates near
+# sigma(0)); 2.0 drives the gates out of the linear regime (|state| up to ~0.9, predictions 0.24-0.44).
+# Larger gains make the recurrence chaotic and amplify the bf16 operand rounding beyond 1e-3
+# (measured table in DESIGN.md), so they are not parity cases.
+@pytest.mark.parametrize("gain,stress", [(1.0, False), (2.0, True)])
+def test_forward_backward_small(gain, stress):
+    B = 24
+    O, cfg, tr, (x, nf, lab), T, S = _setup(SMALL, B, gain, stress=stress)
+    xd = torch.from_numpy(x).cuda()
+    nfd = torch.from_numpy(nf).cuda()
+    labd = torch.from_numpy(lab).cuda()
+    tr.forward_backward(xd, nfd, labd.view(torch.uint8))
+    torch.cuda.synchronize()
+    kw = dict(vocab_size=cfg.vocab_size, num_mixtures=cfg.num_mixtures)
+    ref = O.teacher_student_train_step(torch.from_numpy(x).double(), nf, torch.from_numpy(lab), T, S, None, None,
+                                       clip_gradient_norm=0.0, regularization_penalty=0.0, **kw)
+    # integer side: exact
+    assert np.array_equal(tr.nf_student.cpu().numpy(), ref["num_frames_student"])
+    # forward
+    for name, mine, theirs in [("teacher_state", tr.t_eng.state, ref["teacher_state"]),
+                               ("student_state", tr.s_eng.state, ref["student_state"])]:
+        err = (mine.cpu().double() - theirs).abs().max().item()
+        assert err < 2e-2, (name, err)
+    for name, mine, theirs in [("teacher_pred", tr.t_eng.pred, ref["teacher_predictions"]),
+                               ("student_pred", tr.s_eng.pred, ref["student_predictions"])]:
+        err = (mine.cpu().double() - theirs).abs().max().item()
+        assert err < 1e-3, (name, err)
+    v = tr.losses.cpu().tolist()
+    for got, key in zip(v[:4], ["teacher_ce", "l_ce", "l_pred", "l_rep"]):
+        want = float(ref[key])
+        assert abs(got - want) <= 0.01 * abs(want) + 1e-5, (key, got, want)
+    # gradients (unclipped, reg term excluded on both sides)
+    for params, grads in [(tr.teacher, ref["teacher_grads"]), (tr.student, ref["student_grads"])]:
+        for n in params.names:
+            g, r = params.g[n].cpu().double(), grads[n]
+            den = r.norm().item()
+            if den < 1e-12:
+                assert g.norm().item() < 1e-6, n
+                continue
+            rel = ((g - r).norm() / den).item()
+            assert rel < 3e-2, (n, rel, den)
+
+
+def test_forward_full_size_edges():
+    """Full model dimensions (1152-d, 1024 cells, 4716 classes), edge-case lengths forced in."""
+    full = dict(feature_size=1152, lstm_cells=1024, vocab_size=4716, num_mixtures=2)
+    B = 16
+    O, cfg, tr, (x, nf, lab), T, S = _setup(full, B, 2.0, stress=True)
+    xd, nfd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda()
+    tr.t_eng.forward(xd, None, True, nfd)
+    from efficientvideoclassification_youtube8m_b200 import ops
+    ops.num_frames_student(nfd, 10, 300, tr.nf_student)
+    tr.s_eng.forward(xd, tr.frame_idx, True, tr.nf_student)
+    torch.cuda.synchronize()
+    xn = O.l2_normalize(torch.from_numpy(x).double())
+    with torch.no_grad():
+        ts, tp = O.teacher_forward(xn, nf, T)
+        nfs = O.num_frames_student(nf, 10)
+        ss, sp = O.student_forward(O.sample_uniform(xn, 10), nfs, S)
+    assert np.array_equal(tr.nf_student.cpu().numpy(), nfs)
+    assert (tr.t_eng.pred.cpu().double() - tp).abs().max().item() < 1e-3
+    assert (tr.s_eng.pred.cpu().double() - sp).abs().max().item() < 1e-3
+    assert (tr.t_eng.state.cpu().double() - ts).abs().max().item() < 2e-2
+    assert (tr.s_eng.state.cpu().double() - ss).abs().max().item() < 2e-2
+
+
+def test_train_steps_loss_curve_small():
+    """A few joint T+S steps (clip + TF-Adam): losses within 1 % of the float64 oracle each step."""
+    B, steps = 16, 6
+    O, cfg, tr, (x, nf, lab), T, S = _setup(SMALL, B, 2.0, stress=True)
+    opt_t, opt_s = O.TFAdam(T), O.TFAdam(S)
+    xd, nfd, labd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda(), torch.from_numpy(lab).cuda()
+    kw = dict(vocab_size=cfg.vocab_size, num_mixtures=cfg.num_mixtures)
+    for it in range(steps):
+        tr.step(xd, nfd, labd)
+        got = tr.fetch()
+        ref = O.teacher_student_train_step(torch.from_numpy(x).double(), nf, torch.from_numpy(lab), T, S,
+                                           opt_t, opt_s, **kw)
+        for key in ["teacher_loss", "student_loss", "l_ce", "l_rep"]:
+            want = float(ref[key])
+            assert abs(got[key] - want) <= 0.01 * abs(want) + 1e-4, (it, key, got[key], want)
+    assert got["global_step"] == 2 * steps
