@@ -92,6 +92,12 @@ class HLstmEngine:
                 num_frames: torch.Tensor) -> None:
         """src f32 [B, T_src, D]; frame_idx int32 [K] / [B,K] / None; num_frames int32|int64 [B]
         (already the *sampled* count for the student).  Fills self.state and self.pred."""
+        self.forward_lstm(src, frame_idx, normalize, num_frames)
+        self.classifier_forward()
+
+    def forward_lstm(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
+                     num_frames: torch.Tensor) -> None:
+        """Both LSTM levels: fills self.state (f32) and self.state_bf16."""
         cfg = self.cfg
         H, D, S = cfg.lstm_cells, cfg.feature_size, cfg.state_size
         B, R1, ell, C = self.B, self.R1, self.ell, self.C
@@ -108,7 +114,6 @@ class HLstmEngine:
         self._cell_fwd(b2, a2.h_all[1:], B * H, H, 1, 1, self.len_l2)
         ops.state_pack(a2.c_all[C], a2.h_all[C], b2.c_all[C], b2.h_all[C], B, H,
                        out_bf16=self.state_bf16, out_f32=self.state)
-        self.classifier_forward()
 
     def classifier_forward(self) -> None:
         """MoeModel on self.state_bf16 -> self.pred (video_level_models.py:423-447)."""
@@ -152,10 +157,13 @@ class HLstmEngine:
         """Gradients of every weight into params.g given dP = dLoss/dpredictions [B,V].
         If dstate_preset, self.dstate already holds dLoss/dstate from other consumers of the
         state (L_REP) and the classifier's contribution is added to it."""
+        self.classifier_backward(dP, dstate_preset)
+        self.lstm_backward()
+
+    def classifier_backward(self, dP: torch.Tensor, dstate_preset: bool = False) -> None:
+        """MoE backward: weight gradients into params.g, d(state) accumulated into self.dstate."""
         p, cfg = self.p, self.cfg
-        H, D, S, V, M = cfg.lstm_cells, cfg.feature_size, cfg.state_size, cfg.vocab_size, cfg.num_mixtures
-        B, R1, ell, C = self.B, self.R1, self.ell, self.C
-        # ---- classifier
+        S, V, M, B = cfg.state_size, cfg.vocab_size, cfg.num_mixtures, self.B
         ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde)
         if not dstate_preset:
             ops.fill_f32(self.dstate, 0.0)
@@ -166,6 +174,12 @@ class HLstmEngine:
         gbe = p.g[p.experts_b]
         ops.fill_f32(gbe, 0.0)
         ops.colsum_bf16(self.dE, B, self.lde, self.ldde, gbe)
+
+    def lstm_backward(self) -> None:
+        """Backward of both LSTM levels given self.dstate = dLoss/d(final state)."""
+        p, cfg = self.p, self.cfg
+        H, D, S = cfg.lstm_cells, cfg.feature_size, cfg.state_size
+        B, R1, ell, C = self.B, self.R1, self.ell, self.C
         # ---- RNN_L2 (cell 1 first: its input gradient feeds cell 0)
         a2, b2 = self.l2
         self._cell_bwd(b2, 1, 1, H, self.len_l2, None, self.dstate, 2 * H, self.scr_l2)

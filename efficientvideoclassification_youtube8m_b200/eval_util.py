@@ -1,0 +1,132 @@
+"""Evaluation helpers with the reference's names and semantics (code_student_uniform/eval_util.py:17-213).
+The per-video top-k selection (eval_util.py:118-124, numpy.argpartition on the host in the
+reference) runs on the GPU (evc_topk, exact); only the k triplets per video leave the device."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .average_precision_calculator import AveragePrecisionCalculator, MeanAveragePrecisionCalculator
+
+
+def flatten(l):
+    return [item for sublist in l for item in sublist]
+
+
+def _dev(predictions, actuals):
+    p = predictions if torch.is_tensor(predictions) else torch.as_tensor(np.asarray(predictions, dtype=np.float32))
+    a = actuals if torch.is_tensor(actuals) else torch.as_tensor(np.asarray(actuals))
+    if not p.is_cuda:
+        p, a = p.cuda(), a.cuda()
+    p = p.to(torch.float32).contiguous()
+    a = (a if a.dtype == torch.uint8 else (a != 0).view(torch.uint8)).contiguous()
+    return p, a
+
+
+def top_k_device(predictions, labels, k=20):
+    """(class idx int32 [B,k], prediction f32 [B,k], label u8 [B,k]) as host numpy arrays."""
+    if k <= 0:
+        raise ValueError("k must be a positive integer.")
+    p, a = _dev(predictions, labels)
+    idx, val, lab = ops.topk(p, min(k, p.shape[1]), a)
+    return idx.cpu().numpy(), val.cpu().numpy(), lab.cpu().numpy()
+
+
+def calculate_hit_at_one(predictions, actuals):
+    """eval_util.py:17-31."""
+    idx, _, lab = top_k_device(predictions, actuals, 1)
+    return float(np.average(lab[:, 0].astype(np.float64)))
+
+
+def calculate_precision_at_equal_recall_rate(predictions, actuals):
+    """eval_util.py:34-59: precision over the top-num_labels predictions of each video."""
+    p, a = _dev(predictions, actuals)
+    num_labels = a.sum(dim=1).cpu().numpy().astype(np.int64)
+    kmax = int(num_labels.max()) if len(num_labels) else 0
+    if kmax == 0:
+        return 0.0
+    _, val, lab = top_k_device(p, a, kmax)
+    agg = 0.0
+    for row in range(p.shape[0]):
+        n = int(num_labels[row])
+        if n == 0:
+            continue                      # argpartition(p, -0)[-0:] = all classes, no label set -> 0
+        agg += float(np.sum(lab[row, :n][val[row, :n] > 0])) / n
+    return agg / p.shape[0]
+
+
+def top_k_triplets(predictions, labels, k=20):
+    """eval_util.py:118-124 for one video: [(class, prediction, label)] (ordered by value here)."""
+    p = torch.as_tensor(np.asarray(predictions, dtype=np.float32)).reshape(1, -1)
+    l = torch.as_tensor(np.asarray(labels)).reshape(1, -1)
+    idx, val, lab = top_k_device(p, l, k)
+    return [(int(i), float(v), float(t)) for i, v, t in zip(idx[0], val[0], lab[0])]
+
+
+def top_k_by_class(predictions, labels, k=20):
+    """eval_util.py:82-116."""
+    if k <= 0:
+        raise ValueError("k must be a positive integer.")
+    p, a = _dev(predictions, labels)
+    num_classes = p.shape[1]
+    idx, val, lab = top_k_device(p, a, k)
+    out_predictions = [[] for _ in range(num_classes)]
+    out_labels = [[] for _ in range(num_classes)]
+    for c, v, t in zip(idx.reshape(-1), val.reshape(-1), lab.reshape(-1)):
+        out_predictions[c].append(float(v))
+        out_labels[c].append(float(t))
+    out_true_positives = a.sum(dim=0).cpu().numpy().astype(np.float64).tolist()
+    return out_predictions, out_labels, out_true_positives
+
+
+def calculate_gap(predictions, actuals, top_k=20):
+    """eval_util.py:61-79 global average precision over the per-video top-k."""
+    gap_calculator = AveragePrecisionCalculator()
+    sparse_predictions, sparse_labels, num_positives = top_k_by_class(predictions, actuals, top_k)
+    gap_calculator.accumulate(flatten(sparse_predictions), flatten(sparse_labels), sum(num_positives))
+    return gap_calculator.peek_ap_at_n()
+
+
+class EvaluationMetrics(object):
+    """eval_util.py:126-213."""
+
+    def __init__(self, num_class, top_k):
+        self.sum_hit_at_one = 0.0
+        self.sum_perr = 0.0
+        self.sum_loss = 0.0
+        self.map_calculator = MeanAveragePrecisionCalculator(num_class)
+        self.global_ap_calculator = AveragePrecisionCalculator()
+        self.top_k = top_k
+        self.num_examples = 0
+
+    def accumulate(self, predictions, labels, loss):
+        batch_size = labels.shape[0]
+        mean_hit_at_one = calculate_hit_at_one(predictions, labels)
+        mean_perr = calculate_precision_at_equal_recall_rate(predictions, labels)
+        mean_loss = float(np.mean(loss.cpu().numpy() if torch.is_tensor(loss) else loss))
+        sparse_predictions, sparse_labels, num_positives = top_k_by_class(predictions, labels, self.top_k)
+        self.map_calculator.accumulate(sparse_predictions, sparse_labels, num_positives)
+        self.global_ap_calculator.accumulate(flatten(sparse_predictions), flatten(sparse_labels), sum(num_positives))
+        self.num_examples += batch_size
+        self.sum_hit_at_one += mean_hit_at_one * batch_size
+        self.sum_perr += mean_perr * batch_size
+        self.sum_loss += mean_loss * batch_size
+        return {"hit_at_one": mean_hit_at_one, "perr": mean_perr, "loss": mean_loss}
+
+    def get(self):
+        if self.num_examples <= 0:
+            raise ValueError("total_sample must be positive.")
+        return {"avg_hit_at_one": self.sum_hit_at_one / self.num_examples,
+                "avg_perr": self.sum_perr / self.num_examples,
+                "avg_loss": self.sum_loss / self.num_examples,
+                "aps": self.map_calculator.peek_map_at_n(),
+                "gap": self.global_ap_calculator.peek_ap_at_n()}
+
+    def clear(self):
+        self.sum_hit_at_one = 0.0
+        self.sum_perr = 0.0
+        self.sum_loss = 0.0
+        self.map_calculator.clear()
+        self.global_ap_calculator.clear()
+        self.num_examples = 0

@@ -1,0 +1,72 @@
+"""Flag side-channel of the reference models (tf.flags globals read inside create_model:
+frame_level_models.py:15-47,218-219,237-238,286-289; video_level_models.py:13-19,421;
+train.py:27-99).  Same names and defaults; set them as attributes or via ``parse``."""
+from __future__ import annotations
+
+
+class _Flags:
+    def __init__(self):
+        object.__setattr__(self, "_defs", {})
+
+    def define(self, name, default, doc=""):
+        self._defs[name] = (default, doc)
+        object.__setattr__(self, name, default)
+
+    def __setattr__(self, name, value):
+        if name not in self._defs:
+            raise AttributeError(f"unknown flag --{name}")
+        object.__setattr__(self, name, value)
+
+    def parse(self, argv):
+        """--name value / --name=value pairs, as the run_*.sh launch lines pass them."""
+        i = 0
+        while i < len(argv):
+            a = argv[i]
+            if not a.startswith("--"):
+                raise ValueError(f"unexpected argument {a}")
+            if "=" in a:
+                k, v = a[2:].split("=", 1)
+                i += 1
+            else:
+                k, v = a[2:], argv[i + 1]
+                i += 2
+            if k not in self._defs:
+                raise AttributeError(f"unknown flag --{k}")
+            d = self._defs[k][0]
+            if isinstance(d, bool):
+                v = str(v).lower() in ("1", "true", "yes")
+            elif isinstance(d, int):
+                v = int(v)
+            elif isinstance(d, float):
+                v = float(v)
+            object.__setattr__(self, k, v)
+
+    def reset(self):
+        for k, (d, _) in self._defs.items():
+            object.__setattr__(self, k, d)
+
+
+FLAGS = _Flags()
+# frame_level_models.py:33-47
+FLAGS.define("video_level_classifier_model", "MoeModel", "classifier applied to the final LSTM state")
+FLAGS.define("lstm_cells", 1024, "Number of LSTM cells.")
+FLAGS.define("lstm_layers", 2, "Number of LSTM layers (reference default 1; every run_*.sh passes 2).")
+FLAGS.define("max_num_frames", 300, "maximum number of frames in a video")
+FLAGS.define("num_inputs_to_lstm", 20, "number of chunks presented to the upper LSTM")
+# video_level_models.py:14-16
+FLAGS.define("moe_num_mixtures", 2, "The number of mixtures (excluding the dummy 'expert') used for MoeModel.")
+# train.py:27-99
+FLAGS.define("model", "HierarchicalLstmModel", "Which architecture to use for the model.")
+FLAGS.define("label_loss", "CrossEntropyLoss", "Which loss function to use for training the model.")
+FLAGS.define("optimizer", "AdamOptimizer", "What optimizer class to use.")
+FLAGS.define("batch_size", 1024, "How many examples to process per batch for training.")
+FLAGS.define("every_n", 1, "every nth frame to be used by student.")
+FLAGS.define("dropout", 0.5, "Dropout Probability (unused by H-LSTM / MoE, SURVEY F15)")
+FLAGS.define("regularization_penalty", 2.0, "weight of the regularization loss")
+FLAGS.define("base_learning_rate", 0.001, "Which learning rate to start with.")
+FLAGS.define("learning_rate_decay", 1.0, "Learning rate decay factor")
+FLAGS.define("learning_rate_decay_examples", 4000000.0, "decay period in examples")
+FLAGS.define("clip_gradient_norm", 1.0, "Norm to clip gradients to.")
+FLAGS.define("top_k", 20, "How many predictions to output per video.")
+FLAGS.define("feature_names", "rgb, audio", "features to use")
+FLAGS.define("feature_sizes", "1024, 128", "lengths of the feature vectors")

@@ -94,6 +94,10 @@ class HLstmParams:
         self.wsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
         self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # autograd handle: the kernels write weight gradients straight into flat_g, the token only makes
+        # torch call the backward of the plugin functions
+        self.token = torch.zeros(1, dtype=torch.float32, device=self.device, requires_grad=True)
+        self.reg_grad_scale = None   # d(total_loss)/d(reg_loss) recorded by losses.regularization_loss
         if seed is not None:
             self.init_glorot(seed, lstm_gain)
 

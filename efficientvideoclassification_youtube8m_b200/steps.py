@@ -63,9 +63,16 @@ class _Base:
     def _world():
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
-    def _allreduce(self, params: HLstmParams):
-        if self._world() > 1:
-            dist.all_reduce(params.flat_g, op=dist.ReduceOp.AVG)
+    def _allreduce(self, params):
+        """Average the flat gradient buffer over the data-parallel ranks (NCCL AVG over NVLink; the
+        gloo backend of the CPU tests has no AVG and uses SUM / world)."""
+        n = self._world()
+        if n > 1:
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(params.flat_g, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(params.flat_g, op=dist.ReduceOp.SUM)
+                params.flat_g.div_(n)
 
     def _check(self, raw, num_frames, labels):
         if raw.dtype != torch.float32 or raw.dim() != 3 or raw.shape[1] != MAX_FRAMES:

@@ -1,0 +1,102 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/evc.h declares (no compute
+calls without a GPU); host-side logic of the plugin surface."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "evc.h")).read()
+    return sorted(set(re.findall(r"\b(evc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    lib = ctypes.CDLL(os.path.join(ROOT, "efficientvideoclassification_youtube8m_b200", "libevc.so"))
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"libevc.so does not export {s}"
+    lib.evc_version.restype = ctypes.c_int
+    assert lib.evc_version() >= 1
+
+
+def test_ctypes_table_matches_header():
+    from efficientvideoclassification_youtube8m_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    src = open(os.path.join(ROOT, "include", "evc.h")).read()
+    for name, argtypes in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", src, re.S)
+        assert m, name
+        args = m.group(1).strip()
+        n = 0 if args in ("void", "") else len(args.split(","))
+        if name == "evc_last_error":
+            n = 0
+        assert n == len(argtypes), (name, n, len(argtypes))
+
+
+def test_variable_names_and_shapes_follow_the_reference_checkpoint_layout():
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig, variable_names, variable_shapes
+    names = variable_names("model_student")
+    assert names[0] == "model_student/RNN_L1/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/kernel"
+    assert names[-1] == "model_student/classifier/experts/biases"
+    shp = variable_shapes("model", ModelConfig())
+    assert shp["model/RNN_L1/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/kernel"] == (2176, 4096)
+    assert shp["model/RNN_L2/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/kernel"] == (5120, 4096)
+    assert shp["model/classifier/gates/weights"] == (4096, 14148)
+    assert shp["model/classifier/experts/weights"] == (4096, 9432)
+    total = sum(int(__import__("numpy").prod(s)) for s in shp.values())
+    assert total == 143271128
+
+
+def test_flags_and_class_lookup():
+    from efficientvideoclassification_youtube8m_b200 import frame_level_models, losses, video_level_models
+    from efficientvideoclassification_youtube8m_b200.flags import FLAGS
+    FLAGS.reset()
+    FLAGS.parse("--model HierarchicalLstmModel --batch_size 256 --num_inputs_to_lstm 20 --lstm_layers 2 "
+                "--every_n 10".split())
+    assert FLAGS.every_n == 10 and FLAGS.batch_size == 256
+    with pytest.raises(AttributeError):
+        FLAGS.parse(["--no_such_flag", "1"])
+
+    def find_class_by_name(name, modules):                 # train.py:179-182
+        modules = [getattr(module, name, None) for module in modules]
+        return next(a for a in modules if a)
+    assert find_class_by_name(FLAGS.model, [frame_level_models, video_level_models])().__class__.__name__ == \
+        "HierarchicalLstmModel"
+    assert isinstance(find_class_by_name(FLAGS.label_loss, [losses])(), losses.BaseLoss)
+    assert getattr(video_level_models, FLAGS.video_level_classifier_model).__name__ == "MoeModel"
+    FLAGS.reset()
+
+
+def test_scope_requires_variable_scope_and_uniform_indices():
+    from efficientvideoclassification_youtube8m_b200 import scope
+    from efficientvideoclassification_youtube8m_b200.steps import uniform_frame_indices
+    with pytest.raises(RuntimeError):
+        scope.root_scope()
+    with scope.variable_scope("model"):
+        with scope.variable_scope("classifier") as full:
+            assert full == "model/classifier" and scope.root_scope() == "model"
+    assert uniform_frame_indices(10) == list(range(0, 300, 10))
+    assert len(uniform_frame_indices(30)) == 10
+
+
+def test_average_precision_calculator_matches_reference_golden():
+    import numpy as np
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.average_precision_calculator import AveragePrecisionCalculator
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "eval_golden.npz"))
+    for case in ("small", "yt8m"):
+        p, y = gold[case + "/predictions"], gold[case + "/labels"]
+        idx, val = O.top_k(p, 20)
+        lab = np.take_along_axis(y, idx, axis=1)
+        calc = AveragePrecisionCalculator()
+        calc.accumulate(val.reshape(-1), lab.reshape(-1), float(y.sum()))
+        assert abs(calc.peek_ap_at_n() - float(gold[case + "/gap"])) < 1e-6
+    with pytest.raises(ValueError):
+        AveragePrecisionCalculator(top_n=-1)
