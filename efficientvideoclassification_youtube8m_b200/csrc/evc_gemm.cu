@@ -46,26 +46,44 @@ static int make_tmap_a(CUtensorMap* m, const void* p, int a_mn, long long ld, in
   return a_mn ? make_tmap(m, p, M, K, ld, 64, 64) : make_tmap(m, p, K, M, ld, 64, BM);
 }
 // logical B[K,N]: b_mn = 0 -> stored [N][K]; b_mn = 1 -> stored [K][N]
-static int make_tmap_b(CUtensorMap* m, const void* p, int b_mn, long long ld, int N, int K, int bn) {
-  return b_mn ? make_tmap(m, p, N, K, ld, 64, 64) : make_tmap(m, p, K, N, ld, 64, bn);
+// (cs = cluster size: a K-major B tile is loaded as cs row slices, one per CTA of the cluster)
+static int make_tmap_b(CUtensorMap* m, const void* p, int b_mn, long long ld, int N, int K, int bn, int cs) {
+  return b_mn ? make_tmap(m, p, N, K, ld, 64, 64) : make_tmap(m, p, K, N, ld, 64, bn / cs);
 }
 
-template <int A_MN, int B_MN, int BN, int EPI>
+constexpr int kCluster = 2;   // CTAs per cluster sharing a multicast B tile
+
+template <int A_MN, int B_MN, int BN, int EPI, int CS>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& args,
                   cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, CS>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  const int work = args.tiles_m * args.tiles_n * args.split_k;
+  const int tiles_mc = (args.tiles_m + CS - 1) / CS;
+  const int work = tiles_mc * args.tiles_n * args.split_k;
   if (work <= 0) return EVC_OK;
-  const int grid = work < num_sms() ? work : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, args);
+  const int max_clusters = num_sms() / CS;
+  const int clusters = work < max_clusters ? work : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CS);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, args);
   count_launch();
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(gemm_kernel)");
   return check_launch("gemm_kernel");
 }
 
@@ -92,12 +110,16 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   CUtensorMap ta, tb;
   int rc = make_tmap_a(&ta, A, a_mn, lda, M, K);
   if (rc) return rc;
-  rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn);
+  const int cs = (g.tiles_m >= 2) ? kCluster : 1;
+  rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn, cs);
   if (rc) return rc;
-#define EVC_DISPATCH(AM, BMN)                                                       \
-  if (a_mn == AM && b_mn == BMN) {                                                   \
-    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE>(ta, ta, tb, g, stream)        \
-                     : launch<AM, BMN, 128, EPI_STORE>(ta, ta, tb, g, stream);       \
+#define EVC_DISPATCH(AM, BMN)                                                                    \
+  if (a_mn == AM && b_mn == BMN) {                                                                \
+    if (cs == 1)                                                                                  \
+      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta, tb, g, stream)                \
+                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta, tb, g, stream);               \
+    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta, tb, g, stream)           \
+                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta, tb, g, stream);          \
   }
   EVC_DISPATCH(0, 0)
   EVC_DISPATCH(0, 1)
@@ -110,6 +132,9 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
 }  // namespace evc
 
 using namespace evc;
+
+static int g_debug = 0;
+extern "C" int evc_debug_set(int flags) { g_debug = flags; return 0; }
 
 extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
                              long long ldb, int M, int N, int K, void* C, int c_is_bf16, long long ldc,
@@ -130,7 +155,8 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
   __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
   const long long RH = static_cast<long long>(rows) * H;
   CUtensorMap tb;
-  int rc = make_tmap_b(&tb, W, 1, 4LL * H, 4 * H, Kx + H, 256);
+  const int cs = (rows > BM) ? kCluster : 1;
+  int rc = make_tmap_b(&tb, W, 1, 4LL * H, 4 * H, Kx + H, 256, cs);
   if (rc) return rc;
   for (int t = 0; t < T; ++t) {
     CUtensorMap ta1, ta2;
@@ -147,13 +173,15 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
     g.kb_total = g.kb_a1 + (t == 0 ? 0 : H / BK);  // h_{-1} = 0: skip the recurrent half at t = 0
     g.kb_per_split = g.kb_total;
     g.bias = bias;
+    g.debug = g_debug;
     g.t = t; g.seq_len = seq_len;
     g.c_prev = (t == 0) ? nullptr : c_all + t * RH;
     g.h_prev = (t == 0) ? nullptr : hb + t * RH;
     g.c_out = c_all + (t + 1) * RH;
     g.h_out = hb + (t + 1) * RH;
     g.gates = gb ? gb + t * RH * 4 : nullptr;
-    rc = launch<0, 1, 256, EPI_LSTM_FWD>(ta1, ta2, tb, g, stream);
+    rc = (cs == 1) ? launch<0, 1, 256, EPI_LSTM_FWD, 1>(ta1, ta2, tb, g, stream)
+                   : launch<0, 1, 256, EPI_LSTM_FWD, kCluster>(ta1, ta2, tb, g, stream);
     if (rc) return rc;
   }
   return EVC_OK;
@@ -171,8 +199,9 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
   __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(dz_all);
   const __nv_bfloat16* wh = static_cast<const __nv_bfloat16*>(W) + static_cast<long long>(Kx) * 4 * H;
   const long long RH = static_cast<long long>(rows) * H;
+  const int cs = (rows > BM) ? kCluster : 1;
   CUtensorMap tb;  // B[k = gate column, n = unit] = Wh[unit][gate column] : stored [N][K] = K-major
-  int rc = make_tmap_b(&tb, wh, 0, 4LL * H, H, 4 * H, 128);
+  int rc = make_tmap_b(&tb, wh, 0, 4LL * H, H, 4 * H, 128, cs);
   if (rc) return rc;
   for (int t = T - 1; t >= 0; --t) {
     const bool last = (t == T - 1);
@@ -200,7 +229,8 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     g.dh_pass_out = dh_pass;
     g.dc_out = dc;
     g.dz_out = zb + t * RH * 4;
-    rc = launch<0, 0, 128, EPI_LSTM_BWD>(ta, ta, tb, g, stream);
+    rc = (cs == 1) ? launch<0, 0, 128, EPI_LSTM_BWD, 1>(ta, ta, tb, g, stream)
+                   : launch<0, 0, 128, EPI_LSTM_BWD, kCluster>(ta, ta, tb, g, stream);
     if (rc) return rc;
   }
   return EVC_OK;

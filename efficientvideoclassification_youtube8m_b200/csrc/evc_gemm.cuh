@@ -24,7 +24,8 @@ enum : int { EPI_STORE = 0, EPI_LSTM_FWD = 1, EPI_LSTM_BWD = 2 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 4;   // one per TMEM lane quarter
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct GemmArgs {
   int M, N;            // output extent (rows, columns) used for masking
@@ -32,6 +33,7 @@ struct GemmArgs {
   int kb_total;        // number of 64-wide k blocks (A1 part + A2 part)
   int kb_a1;           // k blocks taken from tensor map A1; the remainder comes from A2
   int kb_per_split;
+  int debug;           // profiling experiments only (evc_debug_set): 1 = epilogue skips math+I/O, 2 = skips global I/O
   // ---- EPI_STORE
   void* C;
   long long ldc;
@@ -64,7 +66,11 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int ACC_STAGES = 2;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // per epilogue warp: accumulator staging, 4 blocks of 32 rows x 16 words (pitch 17) for the LSTM
+  // forward (one per gate) or one block of 32 x 32 (pitch 33) for the backward
+  static constexpr int EPI_STAGE_WORDS = 4 * 32 * 17;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + EPI_WARPS * EPI_STAGE_WORDS * 4;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
@@ -111,22 +117,139 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float* v) {
   *reinterpret_cast<uint4*>(p + 8) = pack8_bf16(v + 8);
 }
 
-template <int A_MN, int B_MN, int BN, int EPI>
+// ---------------------------------------------------------------------------------------------
+// Epilogue I/O staging.  A TMEM lane is an output ROW, so an epilogue thread owns one row and 16
+// consecutive columns of it; accessing global memory that way costs 32 cache-line wavefronts per
+// warp instruction and serialises on the LSU (measured: +30 us per 98 us launch).  The epilogue
+// therefore transposes [32 rows x 16 columns] blocks through a padded per-warp shared-memory
+// area: global accesses are made by 4 (f32) / 2 (bf16) lanes per row segment with 16-byte
+// vectors, all stores of a chunk are issued back to back after ONE warp sync, and the inputs of
+// the next chunk are fetched into registers while the current chunk is being stored.
+// Block layouts in the staging area (32-bit words): f32 block = 32 rows x 16, pitch 17;
+// bf16 block = 32 rows x 8, pitch 9.  `g` = (first row of the warp, first column of the chunk).
+constexpr int STG_F32 = 0;             // word offset of the f32 block
+constexpr int STG_BF16 = 32 * 17;      // word offset of bf16 block 0 (blocks are 288 words apart)
+constexpr int STG_BF16_SZ = 32 * 9;
+
+struct F32Frag { float4 x[4]; };       // what one lane moves for a 32x16 f32 block
+struct Bf16Frag { uint4 x[2]; };       // ... for a 32x16 bf16 block
+
+__device__ __forceinline__ F32Frag fetch_f32(const float* g, long long ld, int nrows, int lane) {
+  F32Frag f;
+  const int pr = lane >> 2, pc = (lane & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = pr + 8 * i;
+    f.x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g != nullptr && r < nrows) f.x[i] = *reinterpret_cast<const float4*>(g + static_cast<long long>(r) * ld + pc);
+  }
+  return f;
+}
+__device__ __forceinline__ Bf16Frag fetch_bf16(const __nv_bfloat16* g, long long ld, int nrows, int lane) {
+  Bf16Frag f;
+  const int pr = lane >> 1, pc = (lane & 1) * 8;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = pr + 16 * i;
+    f.x[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (g != nullptr && r < nrows) f.x[i] = *reinterpret_cast<const uint4*>(g + static_cast<long long>(r) * ld + pc);
+  }
+  return f;
+}
+// fragment -> staging (coalesced orientation)
+__device__ __forceinline__ void stage_in_f32(float* st, const F32Frag& f, int lane) {
+  const int pr = lane >> 2, pc = (lane & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* s = st + (pr + 8 * i) * 17 + pc;
+    s[0] = f.x[i].x; s[1] = f.x[i].y; s[2] = f.x[i].z; s[3] = f.x[i].w;
+  }
+}
+__device__ __forceinline__ void stage_in_bf16(float* st, const Bf16Frag& f, int lane) {
+  uint32_t* s0 = reinterpret_cast<uint32_t*>(st);
+  const int pr = lane >> 1, pc = (lane & 1) * 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t* s = s0 + (pr + 16 * i) * 9 + pc;
+    s[0] = f.x[i].x; s[1] = f.x[i].y; s[2] = f.x[i].z; s[3] = f.x[i].w;
+  }
+}
+// staging -> the 16 values of this lane's row
+__device__ __forceinline__ void stage_get_f32(const float* st, int lane, float* v) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = st[lane * 17 + j];
+}
+__device__ __forceinline__ void stage_get_bf16(const float* st, int lane, float* v) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(st) + lane * 9;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t w = s[j];
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+// this lane's row -> staging
+__device__ __forceinline__ void stage_put_f32(float* st, int lane, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) st[lane * 17 + j] = v[j];
+}
+__device__ __forceinline__ void stage_put_bf16(float* st, int lane, const float* v) {
+  uint32_t* s = reinterpret_cast<uint32_t*>(st) + lane * 9;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    s[j] = *reinterpret_cast<uint32_t*>(&b);
+  }
+}
+// staging -> global (coalesced orientation)
+__device__ __forceinline__ void flush_f32(const float* st, float* g, long long ld, int nrows, int lane) {
+  const int pr = lane >> 2, pc = (lane & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = pr + 8 * i;
+    const float* s = st + r * 17 + pc;
+    if (r < nrows)
+      *reinterpret_cast<float4*>(g + static_cast<long long>(r) * ld + pc) = make_float4(s[0], s[1], s[2], s[3]);
+  }
+}
+__device__ __forceinline__ void flush_bf16(const float* st, __nv_bfloat16* g, long long ld, int nrows, int lane) {
+  const uint32_t* s0 = reinterpret_cast<const uint32_t*>(st);
+  const int pr = lane >> 1, pc = (lane & 1) * 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = pr + 16 * i;
+    const uint32_t* s = s0 + r * 9 + pc;
+    if (r < nrows)
+      *reinterpret_cast<uint4*>(g + static_cast<long long>(r) * ld + pc * 2) = make_uint4(s[0], s[1], s[2], s[3]);
+  }
+}
+
+// CS = cluster size along M: the CS CTAs of a cluster work on M-adjacent tiles of the same N
+// block, each loads 1/CS of the B tile and multicasts it to all of them (L2 -> SM operand
+// traffic per CTA drops from A+B to A+B/CS; the kernel is L2-bandwidth bound without it).
+template <int A_MN, int B_MN, int BN, int EPI, int CS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + Cfg::ACC_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::ACC_STAGES);
+  float* epi_stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CS) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -134,31 +257,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CS);   // every CTA of the cluster must have consumed the slot
     }
     for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast reaches them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_work = args.tiles_m * args.tiles_n * args.split_k;
+  // work item = CS M-adjacent tiles (one per CTA of the cluster); tiles past tiles_m are all-OOB dummies
+  const int tiles_mc = (args.tiles_m + CS - 1) / CS;
+  const int num_work = tiles_mc * args.tiles_n * args.split_k;
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int m_blk = w % args.tiles_m;
-        const int n_blk = (w / args.tiles_m) % args.tiles_n;
-        const int ks = w / (args.tiles_m * args.tiles_n);
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const int m_blk = (w % tiles_mc) * CS + cta_rank;
+        const int n_blk = (w / tiles_mc) % args.tiles_n;
+        const int ks = w / (tiles_mc * args.tiles_n);
         const int kb0 = ks * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -177,13 +303,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           }
           const int kbk = kb * BK;
           if (B_MN) {
+            constexpr int NB = BN / 64;            // 64-column boxes of the B tile; this CTA loads NB/CS
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) {
-              int n = (EPI == EPI_LSTM_FWD) ? (i * args.H + n_blk * 64) : (n_blk * BN + i * 64);
-              tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], n, kbk);
+            for (int j = 0; j < NB / CS; ++j) {
+              const int i = cta_rank * (NB / CS) + j;
+              const int n = (EPI == EPI_LSTM_FWD) ? (i * args.H + n_blk * 64) : (n_blk * BN + i * 64);
+              if (CS > 1) tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[stage], n, kbk, kMcMask);
+              else tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], n, kbk);
             }
           } else {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kbk, n_blk * BN);
+            constexpr int RB = BN / CS;            // rows of the K-major B tile loaded by this CTA
+            if (CS > 1) tma_load_2d_mc(sb + cta_rank * RB * 128, &tmB, &full_bar[stage], kbk,
+                                       n_blk * BN + cta_rank * RB, kMcMask);
+            else tma_load_2d(sb, &tmB, &full_bar[stage], kbk, n_blk * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -196,8 +328,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        const int ks = w / (args.tiles_m * args.tiles_n);
+      for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
+        const int ks = w / (tiles_mc * args.tiles_n);
         const int kb0 = ks * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         const int as = it & 1;
@@ -216,7 +348,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CS > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (kb1 > kb0) umma_commit(&tfull_bar[as]);
@@ -225,203 +358,279 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
   } else {
     // ===================================================== epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    float* stage = epi_stage_base + (warp - 2) * Cfg::EPI_STAGE_WORDS;
+    float* st_f = stage + STG_F32;
+    float* st_b0 = stage + STG_BF16;
     int it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      const int m_blk = w % args.tiles_m;
-      const int n_blk = (w / args.tiles_m) % args.tiles_n;
-      const int ks = w / (args.tiles_m * args.tiles_n);
+    for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
+      const int m_blk = (w % tiles_mc) * CS + cta_rank;
+      const int n_blk = (w / tiles_mc) % args.tiles_n;
+      const int ks = w / (tiles_mc * args.tiles_n);
       const bool has_acc = min(args.kb_total, (ks + 1) * args.kb_per_split) > ks * args.kb_per_split;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row0 = m_blk * BM + q * 32;          // first row of this warp
+      const int row = row0 + lane;
+      const int nrows = args.M - row0;               // valid rows of this warp (may be <= 0 or > 32)
       const bool row_ok = row < args.M;
 
       if constexpr (EPI == EPI_STORE) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
           const int col0 = n_blk * BN + c0;
-          if (row_ok && col0 < args.N) {
-            float v[32];
+          if (col0 >= args.N || nrows <= 0) continue;   // warp-uniform
+          float v[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (args.bias != nullptr && ks == 0) {
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (args.bias != nullptr && ks == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < args.N) v[j] += __ldg(args.bias + col0 + j);
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < args.N) v[j] += __ldg(args.bias + col0 + j);
+          }
+          const bool full = (col0 + 16 <= args.N);
+          if (args.c_bf16) {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(args.C) + static_cast<long long>(row0) * args.ldc + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(cp) | (args.ldc * 2)) & 15) == 0) {
+              stage_put_bf16(st_b0, lane, v);
+              __syncwarp();
+              flush_bf16(st_b0, cp, args.ldc, nrows, lane);
+              __syncwarp();
+            } else if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < args.N) cp[static_cast<long long>(lane) * args.ldc + j] = __float2bfloat16(v[j]);
             }
-            const bool full = (col0 + 32 <= args.N);
-            if (args.atomic_add) {
-              float* cp = reinterpret_cast<float*>(args.C) + static_cast<long long>(row) * args.ldc + col0;
+          } else {
+            float* cp = reinterpret_cast<float*>(args.C) + static_cast<long long>(row0) * args.ldc + col0;
+            const bool vec = full && ((reinterpret_cast<uintptr_t>(cp) | (args.ldc * 4)) & 15) == 0;
+            if (!args.atomic_add && vec) {
+              stage_put_f32(st_f, lane, v);
+              __syncwarp();
+              flush_f32(st_f, cp, args.ldc, nrows, lane);
+              __syncwarp();
+            } else if (args.atomic_add) {
+              stage_put_f32(st_f, lane, v);
+              __syncwarp();
+              const int pr = lane >> 2, pc = (lane & 3) * 4;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || col0 + j < args.N) atomicAdd(cp + j, v[j]);
-            } else if (args.c_bf16) {
-              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(args.C) + static_cast<long long>(row) * args.ldc + col0;
-              if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-                store16_bf16(cp, v);
-                store16_bf16(cp + 16, v + 16);
-              } else {
+              for (int i = 0; i < 4; ++i) {
+                const int rr = pr + 8 * i;
+                if (rr < nrows) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < args.N) cp[j] = __float2bfloat16(v[j]);
+                  for (int k = 0; k < 4; ++k)
+                    if (col0 + pc + k < args.N)
+                      atomicAdd(cp + static_cast<long long>(rr) * args.ldc + pc + k, st_f[rr * 17 + pc + k]);
+                }
               }
-            } else {
-              float* cp = reinterpret_cast<float*>(args.C) + static_cast<long long>(row) * args.ldc + col0;
-              if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-                store16_f32(cp, v);
-                store16_f32(cp + 16, v + 16);
-              } else {
+              __syncwarp();
+            } else if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < args.N) cp[j] = v[j];
-              }
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < args.N) cp[static_cast<long long>(lane) * args.ldc + j] = v[j];
             }
           }
         }
       } else if constexpr (EPI == EPI_LSTM_FWD) {
-        // accumulator columns: [g*64 + u], gate g in (i, j, f, o), unit u of this tile
+        // Accumulator columns: [g*64 + u], gate g in (i, j, f, o), unit u of this tile.  The f32
+        // accumulators are transposed through shared memory (one TMEM lane = one row), then every
+        // lane owns 4 consecutive units of a row: all global accesses are 8/16-byte vectors with
+        // 4 lanes covering one 64-byte row segment (8 row segments per warp instruction).
         const int H = args.H;
-        const bool live = row_ok && (args.t < __ldg(args.seq_len + (row_ok ? row : 0)));
+        const int pr = lane >> 2, pc = (lane & 3) * 4;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
 #pragma unroll 1
         for (int cu = 0; cu < 64; cu += 16) {
-          uint32_t ri[16], rj[16], rf[16], ro[16];
-          tmem_ld16(taddr + 0 * 64 + cu, ri);
-          tmem_ld16(taddr + 1 * 64 + cu, rj);
-          tmem_ld16(taddr + 2 * 64 + cu, rf);
-          tmem_ld16(taddr + 3 * 64 + cu, ro);
-          tmem_ld_wait();
-          const int u0 = n_blk * 64 + cu;
-          if (row_ok) {
-            const long long off = static_cast<long long>(row) * H + u0;
-            float cp[16];
-            if (args.c_prev != nullptr) load16_f32(args.c_prev + off, cp);
-            else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) cp[j] = 0.f;
-            }
-            if (live) {
-              float gi[16], gj[16], gf[16], go[16], cn[16], hn[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float zi = __uint_as_float(ri[j]) + __ldg(args.bias + 0 * H + u0 + j);
-                const float zj = __uint_as_float(rj[j]) + __ldg(args.bias + 1 * H + u0 + j);
-                const float zf = __uint_as_float(rf[j]) + __ldg(args.bias + 2 * H + u0 + j);
-                const float zo = __uint_as_float(ro[j]) + __ldg(args.bias + 3 * H + u0 + j);
-                gi[j] = sigmoid_f(zi);
-                gj[j] = tanh_f(zj);
-                gf[j] = sigmoid_f(zf + 1.0f);  // forget_bias = 1.0 added at use
-                go[j] = sigmoid_f(zo);
-                cn[j] = cp[j] * gf[j] + gi[j] * gj[j];
-                hn[j] = tanh_f(cn[j]) * go[j];
-              }
-              store16_f32(args.c_out + off, cn);
-              store16_bf16(args.h_out + off, hn);
-              if (args.gates != nullptr) {
-                __nv_bfloat16* gp = args.gates + static_cast<long long>(row) * 4 * H + u0;
-                store16_bf16(gp + 0 * H, gi);
-                store16_bf16(gp + 1 * H, gj);
-                store16_bf16(gp + 2 * H, gf);
-                store16_bf16(gp + 3 * H, go);
-              }
-            } else {
-              // dynamic_rnn: rows past their sequence_length keep their state
-              store16_f32(args.c_out + off, cp);
-              uint4 a = make_uint4(0, 0, 0, 0), b = a;
-              if (args.h_prev != nullptr) {
-                a = *reinterpret_cast<const uint4*>(args.h_prev + off);
-                b = *reinterpret_cast<const uint4*>(args.h_prev + off + 8);
-              }
-              *reinterpret_cast<uint4*>(args.h_out + off) = a;
-              *reinterpret_cast<uint4*>(args.h_out + off + 8) = b;
-            }
-          }
-        }
-      } else {  // EPI_LSTM_BWD : accumulator = dz_{t+1} * Wh^T, columns = hidden units of this tile
-        const int H = args.H;
-        const int len = row_ok ? __ldg(args.seq_len + row) : 0;
-        const bool live = row_ok && (args.t < len);
-        const bool had_pass = (args.t + 1 >= len);  // row was masked at step t+1 (or t is the last step)
-#pragma unroll 1
-        for (int cu = 0; cu < BN; cu += 16) {
-          uint32_t racc[16];
-          if (has_acc) {
-            tmem_ld16(taddr + cu, racc);
+          {
+            uint32_t ri[16], rj[16], rf[16], ro[16];
+            tmem_ld16(taddr + 0 * 64 + cu, ri);
+            tmem_ld16(taddr + 1 * 64 + cu, rj);
+            tmem_ld16(taddr + 2 * 64 + cu, rf);
+            tmem_ld16(taddr + 3 * 64 + cu, ro);
             tmem_ld_wait();
-          } else {
+            if (args.debug == 1) continue;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) racc[j] = 0u;
+            for (int j = 0; j < 16; ++j) {
+              stage[0 * 544 + lane * 17 + j] = __uint_as_float(ri[j]);
+              stage[1 * 544 + lane * 17 + j] = __uint_as_float(rj[j]);
+              stage[2 * 544 + lane * 17 + j] = __uint_as_float(rf[j]);
+              stage[3 * 544 + lane * 17 + j] = __uint_as_float(ro[j]);
+            }
           }
-          const int u0 = n_blk * BN + cu;
-          if (row_ok && u0 < H) {
-            const long long off = static_cast<long long>(row) * H + u0;
-            float dh[16], dc[16];
+          __syncwarp();
+          const int u = n_blk * 64 + cu + pc;               // first of this lane's 4 units
+          const float4 bi = __ldg(reinterpret_cast<const float4*>(args.bias + 0 * H + u));
+          const float4 bj = __ldg(reinterpret_cast<const float4*>(args.bias + 1 * H + u));
+          const float4 bf = __ldg(reinterpret_cast<const float4*>(args.bias + 2 * H + u));
+          const float4 bo = __ldg(reinterpret_cast<const float4*>(args.bias + 3 * H + u));
+          const float bia[4][4] = {{bi.x, bi.y, bi.z, bi.w}, {bj.x, bj.y, bj.z, bj.w},
+                                   {bf.x, bf.y, bf.z, bf.w}, {bo.x, bo.y, bo.z, bo.w}};
+          float4 cpv[4];
+          bool okr[4], liver[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dh[j] = __uint_as_float(racc[j]);
-            if (args.dh_ext != nullptr) {
-              float e[16];
-              load16_f32(args.dh_ext + static_cast<long long>(row) * args.ld_dh_ext + u0, e);
+          for (int i = 0; i < 4; ++i) {                     // issue all independent loads first
+            const int r = row0 + pr + 8 * i;
+            okr[i] = r < args.M;
+            liver[i] = okr[i] && (args.t < __ldg(args.seq_len + (okr[i] ? r : 0)));
+            cpv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (okr[i] && args.c_prev != nullptr && !(args.debug & 4))
+              cpv[i] = *reinterpret_cast<const float4*>(args.c_prev + static_cast<long long>(r) * H + u);
+          }
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dh[j] += e[j];
+          for (int i = 0; i < 4; ++i) {
+            const int rl = pr + 8 * i;
+            const int r = row0 + rl;
+            const float* sp = stage + rl * 17 + pc;
+            const float cp[4] = {cpv[i].x, cpv[i].y, cpv[i].z, cpv[i].w};
+            float cn[4], hn[4], g4[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              g4[0][k] = sigmoid_f(sp[0 * 544 + k] + bia[0][k]);
+              g4[1][k] = tanh_f(sp[1 * 544 + k] + bia[1][k]);
+              g4[2][k] = sigmoid_f(sp[2 * 544 + k] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
+              g4[3][k] = sigmoid_f(sp[3 * 544 + k] + bia[3][k]);
+              cn[k] = cp[k] * g4[2][k] + g4[0][k] * g4[1][k];
+              hn[k] = tanh_f(cn[k]) * g4[3][k];
             }
-            if (had_pass && args.dh_pass_in != nullptr) {
-              float e[16];
-              load16_f32(args.dh_pass_in + static_cast<long long>(row) * args.ld_dh_pass_in + u0, e);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dh[j] += e[j];
+            if (!okr[i]) continue;
+            const long long off = static_cast<long long>(r) * H + u;
+            if (!liver[i]) {
+              // dynamic_rnn: rows past their sequence_length keep their state
+              uint2 hp = make_uint2(0u, 0u);
+              if (args.h_prev != nullptr) hp = *reinterpret_cast<const uint2*>(args.h_prev + off);
+              *reinterpret_cast<float4*>(args.c_out + off) = cpv[i];
+              *reinterpret_cast<uint2*>(args.h_out + off) = hp;
+              continue;
             }
-            if (args.dc_in != nullptr) load16_f32(args.dc_in + static_cast<long long>(row) * args.ld_dc_in + u0, dc);
-            else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dc[j] = 0.f;
+            if (args.debug == 2) {
+              if (cn[0] + hn[1] + g4[0][2] + g4[1][3] + g4[2][0] + g4[3][1] == 123.456f) args.c_out[0] = cn[0];
+              continue;
             }
-            __nv_bfloat16* zp = args.dz_out + static_cast<long long>(row) * 4 * H + u0;
-            if (live) {
-              float gi[16], gj[16], gf[16], go[16], cp[16];
-              const __nv_bfloat16* gp = args.gates + static_cast<long long>(row) * 4 * H + u0;
-              load16_bf16(gp + 0 * H, gi);
-              load16_bf16(gp + 1 * H, gj);
-              load16_bf16(gp + 2 * H, gf);
-              load16_bf16(gp + 3 * H, go);
-              if (args.c_prev != nullptr) load16_f32(args.c_prev + off, cp);
-              else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) cp[j] = 0.f;
-              }
-              float di[16], dj[16], df[16], dout[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float cn = cp[j] * gf[j] + gi[j] * gj[j];
-                const float tc = tanh_f(cn);
-                dout[j] = dh[j] * tc * go[j] * (1.f - go[j]);
-                const float dcn = dc[j] + dh[j] * go[j] * (1.f - tc * tc);
-                di[j] = dcn * gj[j] * gi[j] * (1.f - gi[j]);
-                dj[j] = dcn * gi[j] * (1.f - gj[j] * gj[j]);
-                df[j] = dcn * cp[j] * gf[j] * (1.f - gf[j]);
-                dc[j] = dcn * gf[j];
-              }
-              store16_bf16(zp + 0 * H, di);
-              store16_bf16(zp + 1 * H, dj);
-              store16_bf16(zp + 2 * H, df);
-              store16_bf16(zp + 3 * H, dout);
-              store16_f32(args.dc_out + off, dc);
-            } else {
-              const uint4 z = make_uint4(0, 0, 0, 0);
+            if (!(args.debug & 16)) {
+              *reinterpret_cast<float4*>(args.c_out + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
+              *reinterpret_cast<uint2*>(args.h_out + off) =
+                  make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+            }
+            if (args.gates != nullptr && !(args.debug & 8)) {
+              __nv_bfloat16* gp = args.gates + static_cast<long long>(r) * 4 * H + u;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                *reinterpret_cast<uint4*>(zp + g * H) = z;
-                *reinterpret_cast<uint4*>(zp + g * H + 8) = z;
+                __nv_bfloat162 a01 = __floats2bfloat162_rn(g4[g][0], g4[g][1]);
+                __nv_bfloat162 a23 = __floats2bfloat162_rn(g4[g][2], g4[g][3]);
+                *reinterpret_cast<uint2*>(gp + g * H) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&a01), *reinterpret_cast<uint32_t*>(&a23));
               }
-              store16_f32(args.dc_out + off, dc);
-              store16_f32(args.dh_pass_out + off, dh);
             }
           }
+          __syncwarp();                                     // staging is overwritten by the next chunk
+        }
+      } else {
+        // EPI_LSTM_BWD: accumulator = dz_{t+1} * Wh^T, columns = hidden units of this tile.  Same scheme:
+        // 32 x 32 accumulator strips are transposed through shared memory, then lane = (row, 4 units).
+        const int H = args.H;
+        const int pr = lane >> 3, pc = (lane & 7) * 4;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cs0 = 0; cs0 < BN; cs0 += 32) {
+          if (n_blk * BN + cs0 >= H) break;                 // warp-uniform
+          if (has_acc) {
+            uint32_t racc[32];
+            tmem_ld32(taddr + cs0, racc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(racc[j]);
+          }
+          __syncwarp();
+          const int u = n_blk * BN + cs0 + pc;              // first of this lane's 4 units
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            // phase A: all loads of 4 lane-iterations are issued before any of them is used
+            uint2 gq[4][4];
+            float4 cpv[4], dcv[4], dhv[4];
+            int lenr[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+              const int r = row0 + pr + 4 * (half * 4 + ii);
+              const int rr = r < args.M ? r : args.M - 1;     // clamp: loads stay in bounds, results unused
+              const long long off = static_cast<long long>(rr) * H + u;
+              lenr[ii] = __ldg(args.seq_len + rr);
+              const __nv_bfloat16* gp = args.gates + static_cast<long long>(rr) * 4 * H + u;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) gq[ii][g] = *reinterpret_cast<const uint2*>(gp + g * H);
+              cpv[ii] = args.c_prev ? *reinterpret_cast<const float4*>(args.c_prev + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+              dcv[ii] = args.dc_in ? *reinterpret_cast<const float4*>(args.dc_in + static_cast<long long>(rr) * args.ld_dc_in + u)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              dhv[ii] = args.dh_ext ? *reinterpret_cast<const float4*>(args.dh_ext + static_cast<long long>(rr) * args.ld_dh_ext + u)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // phase B: gate gradients
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+              const int rl = pr + 4 * (half * 4 + ii);
+              const int r = row0 + rl;
+              if (r >= args.M) continue;
+              const int len = lenr[ii];
+              const bool live = args.t < len;
+              const long long off = static_cast<long long>(r) * H + u;
+              float dh[4] = {dhv[ii].x, dhv[ii].y, dhv[ii].z, dhv[ii].w};
+              float dc[4] = {dcv[ii].x, dcv[ii].y, dcv[ii].z, dcv[ii].w};
+              if (has_acc) {
+                const float* sp = stage + rl * 33 + pc;
+                dh[0] += sp[0]; dh[1] += sp[1]; dh[2] += sp[2]; dh[3] += sp[3];
+              }
+              if (args.t + 1 >= len && args.dh_pass_in != nullptr) {   // masked at step t+1 (or t is the last step)
+                const float4 e = *reinterpret_cast<const float4*>(args.dh_pass_in + static_cast<long long>(r) * args.ld_dh_pass_in + u);
+                dh[0] += e.x; dh[1] += e.y; dh[2] += e.z; dh[3] += e.w;
+              }
+              __nv_bfloat16* zp = args.dz_out + static_cast<long long>(r) * 4 * H + u;
+              if (live) {
+                float g4[4][4];
+                const float cp[4] = {cpv[ii].x, cpv[ii].y, cpv[ii].z, cpv[ii].w};
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq[ii][g].x));
+                  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq[ii][g].y));
+                  g4[g][0] = a.x; g4[g][1] = a.y; g4[g][2] = b.x; g4[g][3] = b.y;
+                }
+                float dz4[4][4], dco[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float gi = g4[0][k], gj = g4[1][k], gf = g4[2][k], go = g4[3][k];
+                  const float cn = cp[k] * gf + gi * gj;
+                  const float tc = tanh_f(cn);
+                  const float dcn = dc[k] + dh[k] * go * (1.f - tc * tc);
+                  dz4[0][k] = dcn * gj * gi * (1.f - gi);
+                  dz4[1][k] = dcn * gi * (1.f - gj * gj);
+                  dz4[2][k] = dcn * cp[k] * gf * (1.f - gf);
+                  dz4[3][k] = dh[k] * tc * go * (1.f - go);
+                  dco[k] = dcn * gf;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  __nv_bfloat162 a01 = __floats2bfloat162_rn(dz4[g][0], dz4[g][1]);
+                  __nv_bfloat162 a23 = __floats2bfloat162_rn(dz4[g][2], dz4[g][3]);
+                  *reinterpret_cast<uint2*>(zp + g * H) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&a01), *reinterpret_cast<uint32_t*>(&a23));
+                }
+                *reinterpret_cast<float4*>(args.dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+              } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
+                *reinterpret_cast<float4*>(args.dc_out + off) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+                *reinterpret_cast<float4*>(args.dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       // release the accumulator stage to the MMA warp
@@ -432,7 +641,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
