@@ -21,8 +21,9 @@ SIGNATURES = {
     "evc_random_frame_index": [P, P, I, I, P, P],
     "evc_random_sequence_index": [P, P, I, I, P, P],
     "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
-    "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P],
-    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P],
+    "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
+    "evc_lstm_workspace_bytes": [I, I, I],
+    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P, L, P],
     "evc_state_pack": [P, P, P, P, I, I, P, P, P],
     "evc_cast_bf16": [P, L, I, I, P, P],
     "evc_fill_f32": [P, L, F, P],
@@ -37,7 +38,8 @@ SIGNATURES = {
     "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P],
     "evc_topk": [P, I, I, I, P, P, P, P, P],
 }
-_RESTYPES = {"evc_last_error": C.c_char_p, "evc_launch_count": C.c_longlong}
+_RESTYPES = {"evc_last_error": C.c_char_p, "evc_launch_count": C.c_longlong,
+             "evc_lstm_workspace_bytes": C.c_longlong}
 
 
 class EvcError(RuntimeError):

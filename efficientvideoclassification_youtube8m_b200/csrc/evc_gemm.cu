@@ -90,36 +90,46 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------ generic GEMM
+// force_bn: 0 = choose, else 128/256.  split_stride != 0: split-K partial slabs instead of atomics
+// (*splits_out receives the number of slabs actually written).
 static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M, int N,
                       int K, void* C, int c_bf16, long long ldc, const float* bias, int split_k, int accumulate,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int force_bn = 0, long long split_stride = 0, int* splits_out = nullptr,
+                      const void* A2 = nullptr, int K1 = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "gemm: empty problem");
   if (split_k < 1) split_k = 1;
   if ((split_k > 1 || accumulate) && c_bf16) return set_error(EVC_ERR_ARG, "gemm: split-K/accumulate needs f32 C");
-  const int bn = (N > 128) ? 256 : 128;
+  const int bn = force_bn ? force_bn : ((N > 128) ? 256 : 128);
   GemmArgs g = {};
   g.M = M; g.N = N;
   g.tiles_m = ceil_div(M, BM);
   g.tiles_n = ceil_div(N, bn);
   g.kb_total = ceil_div(K, BK);
-  g.kb_a1 = g.kb_total;
+  g.kb_a1 = A2 ? K1 / BK : g.kb_total;          // A = [A1 (K1 columns) | A2] concatenated along K
   g.kb_per_split = ceil_div(g.kb_total, split_k);
   g.split_k = ceil_div(g.kb_total, g.kb_per_split);
   g.C = C; g.ldc = ldc; g.c_bf16 = c_bf16; g.bias = bias;
-  g.atomic_add = (g.split_k > 1 || accumulate) ? 1 : 0;
-  CUtensorMap ta, tb;
-  int rc = make_tmap_a(&ta, A, a_mn, lda, M, K);
+  g.split_stride = split_stride;
+  g.atomic_add = (split_stride == 0 && (g.split_k > 1 || accumulate)) ? 1 : 0;
+  if (splits_out) *splits_out = g.split_k;
+  CUtensorMap ta, ta2, tb;
+  int rc = make_tmap_a(&ta, A, a_mn, A2 ? K1 : lda, M, A2 ? K1 : K);
   if (rc) return rc;
+  ta2 = ta;
+  if (A2) {
+    rc = make_tmap_a(&ta2, A2, a_mn, K - K1, M, K - K1);
+    if (rc) return rc;
+  }
   const int cs = (g.tiles_m >= 2) ? kCluster : 1;
   rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn, cs);
   if (rc) return rc;
 #define EVC_DISPATCH(AM, BMN)                                                                    \
   if (a_mn == AM && b_mn == BMN) {                                                                \
     if (cs == 1)                                                                                  \
-      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta, tb, g, stream)                \
-                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta, tb, g, stream);               \
-    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta, tb, g, stream)           \
-                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta, tb, g, stream);          \
+      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta2, tb, g, stream)               \
+                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta2, tb, g, stream);              \
+    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta2, tb, g, stream)          \
+                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta2, tb, g, stream);         \
   }
   EVC_DISPATCH(0, 0)
   EVC_DISPATCH(0, 1)
@@ -144,9 +154,26 @@ extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
 }
 
 // ------------------------------------------------------------------ BasicLSTM layer, forward over T steps
+// split-K factor for a recurrence step whose output has `tiles` tiles: fill the SMs, keep >= 8 k blocks
+static int pick_split(int tiles, int kb_total) {
+  int s = num_sms() / (tiles > 0 ? tiles : 1);
+  if (s > 8) s = 8;
+  while (s > 1 && kb_total / s < 8) --s;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
+  // forward small-row path: S x rows x 4H f32 ; backward: S x rows x H f32
+  const int sf = (rows <= 1024) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
+  const int sb = pick_split(ceil_div(rows, BM) * (H / 128), 4 * H / BK);
+  const long long f = static_cast<long long>(sf) * rows * 4 * H * 4;
+  const long long b = static_cast<long long>(sb) * rows * H * 4;
+  return (f > b ? f : b) + 256;
+}
+
 extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
                                 int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
-                                void* gates_all, void* stream_) {
+                                void* gates_all, void* workspace, long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: empty problem");
   if (H % 64 != 0 || Kx % 64 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: H and Kx must be multiples of 64");
@@ -154,9 +181,32 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
   __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h_all);
   __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
   const long long RH = static_cast<long long>(rows) * H;
-  CUtensorMap tb;
+  int rc;
+  if (rows <= 1024 && workspace != nullptr) {
+    // Small-row steps (RNN_L2, student): one 128x256 tile per CTA would serialise the whole K on a few
+    // SMs.  Split K over the SMs into f32 partial slabs, then one full-occupancy cell kernel sums
+    // the slabs and applies bias / gates / state update / length mask.
+    float* part = static_cast<float*>(workspace);
+    const long long slab = static_cast<long long>(rows) * 4 * H;
+    for (int t = 0; t < T; ++t) {
+      const int K = Kx + (t == 0 ? 0 : H);          // h_{-1} = 0: skip the recurrent half at t = 0
+      const int want = pick_split(ceil_div(rows, BM) * (4 * H / 256), K / BK);
+      if (static_cast<long long>(want) * slab * 4 > workspace_bytes)
+        return set_error(EVC_ERR_ARG, "lstm_seq_fwd: workspace too small (evc_lstm_workspace_bytes)");
+      int splits = 1;
+      rc = gemm_store(xb + t * x_step_stride, 0, Kx, W, 1, 4LL * H, rows, 4 * H, K, part, 0, 4LL * H, nullptr, want, 0,
+                      stream, 256, slab, &splits, (t == 0) ? nullptr : hb + t * RH, Kx);
+      if (rc) return rc;
+      rc = launch_lstm_cell_fwd(part, splits, slab, bias, (t == 0) ? nullptr : c_all + t * RH,
+                                (t == 0) ? nullptr : hb + t * RH, seq_len, t, rows, H, c_all + (t + 1) * RH,
+                                hb + (t + 1) * RH, gb ? gb + t * RH * 4 : nullptr, stream);
+      if (rc) return rc;
+    }
+    return EVC_OK;
+  }
   const int cs = (rows > BM) ? kCluster : 1;
-  int rc = make_tmap_b(&tb, W, 1, 4LL * H, 4 * H, Kx + H, 256, cs);
+  CUtensorMap tb;
+  rc = make_tmap_b(&tb, W, 1, 4LL * H, 4 * H, Kx + H, 256, cs);
   if (rc) return rc;
   for (int t = 0; t < T; ++t) {
     CUtensorMap ta1, ta2;
@@ -191,7 +241,8 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
 extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len,
                                 const void* gates_all, const float* c_all, const float* dh_ext_all,
                                 const float* dh_final, long long ld_dh_final, const float* dc_final,
-                                long long ld_dc_final, float* dh_pass, float* dc, void* dz_all, void* stream_) {
+                                long long ld_dc_final, float* dh_pass, float* dc, void* dz_all, void* workspace,
+                                long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: empty problem");
   if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: H must be a multiple of 128");
@@ -199,6 +250,30 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
   __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(dz_all);
   const __nv_bfloat16* wh = static_cast<const __nv_bfloat16*>(W) + static_cast<long long>(Kx) * 4 * H;
   const long long RH = static_cast<long long>(rows) * H;
+  if (workspace != nullptr) {
+    // Recurrent dgrad dh = dz_{t+1} Wh^T as a (split-K) GEMM into f32 slabs + a full-occupancy cell
+    // kernel.  Measured faster than the fused epilogue at every row count: the cell backward moves
+    // 36 B per element, which 4 epilogue warps per SM cannot keep in flight behind a 4096-deep GEMM.
+    float* part = static_cast<float*>(workspace);
+    const int want = pick_split(ceil_div(rows, BM) * (H / 128), 4 * H / BK);
+    if (static_cast<long long>(want) * RH * 4 > workspace_bytes)
+      return set_error(EVC_ERR_ARG, "lstm_seq_bwd: workspace too small (evc_lstm_workspace_bytes)");
+    for (int t = T - 1; t >= 0; --t) {
+      const bool last = (t == T - 1);
+      int splits = 0;
+      if (!last) {
+        int rc = gemm_store(zb + (t + 1) * RH * 4, 0, 4LL * H, wh, 0, 4LL * H, rows, H, 4 * H, part, 0, H, nullptr,
+                            want, 0, stream, 128, RH, &splits);
+        if (rc) return rc;
+      }
+      int rc = launch_lstm_cell_bwd(part, splits, RH, gb + t * RH * 4, (t == 0) ? nullptr : c_all + t * RH,
+                                    dh_ext_all ? dh_ext_all + t * RH : nullptr, H, last ? dh_final : dh_pass,
+                                    last ? ld_dh_final : H, last ? dc_final : dc, last ? ld_dc_final : H, seq_len, t,
+                                    rows, H, zb + t * RH * 4, dc, dh_pass, stream);
+      if (rc) return rc;
+    }
+    return EVC_OK;
+  }
   const int cs = (rows > BM) ? kCluster : 1;
   CUtensorMap tb;  // B[k = gate column, n = unit] = Wh[unit][gate column] : stored [N][K] = K-major
   int rc = make_tmap_b(&tb, wh, 0, 4LL * H, H, 4 * H, 128, cs);

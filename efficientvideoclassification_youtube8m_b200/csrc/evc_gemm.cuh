@@ -39,6 +39,7 @@ struct GemmArgs {
   long long ldc;
   int c_bf16;          // 0: float, 1: bf16
   int atomic_add;      // 1: red.add.f32 into C (split-K or accumulate)
+  long long split_stride;  // != 0: split ks stores its partial product at C + ks*split_stride (no atomics)
   const float* bias;   // [N] or null
   // ---- EPI_LSTM_FWD / BWD (row r, hidden unit u; H = N/4 for fwd, N for bwd)
   int H;
@@ -408,7 +409,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                 if (col0 + j < args.N) cp[static_cast<long long>(lane) * args.ldc + j] = __float2bfloat16(v[j]);
             }
           } else {
-            float* cp = reinterpret_cast<float*>(args.C) + static_cast<long long>(row0) * args.ldc + col0;
+            float* cp = reinterpret_cast<float*>(args.C) + ks * args.split_stride +
+                        static_cast<long long>(row0) * args.ldc + col0;
             const bool vec = full && ((reinterpret_cast<uintptr_t>(cp) | (args.ldc * 4)) & 15) == 0;
             if (!args.atomic_add && vec) {
               stage_put_f32(st_f, lane, v);

@@ -145,6 +145,149 @@ __global__ void state_pack_kernel(const float* __restrict__ c0, const __nv_bfloa
   }
 }
 
+__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+__device__ __forceinline__ void unpack4_bf16(uint2 w, float* v) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// BasicLSTMCell forward on split-K partial pre-activations (small-row recurrence steps):
+//   z = sum_s z_part[s] + bias ; i,j,f,o ; c' = c*sigmoid(f+1) + sigmoid(i)*tanh(j) ; h' = tanh(c')*sigmoid(o)
+// with the dynamic_rnn copy-through for rows past their sequence_length.  Thread = (row, 4 units).
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, long long part_stride,
+                                     const float* __restrict__ bias, const float* __restrict__ c_prev,
+                                     const __nv_bfloat16* __restrict__ h_prev, const int* __restrict__ seq_len,
+                                     int t, int rows, int H, float* __restrict__ c_out,
+                                     __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ gates) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int hq = H >> 2;
+  if (idx >= static_cast<long long>(rows) * hq) return;
+  const int r = static_cast<int>(idx / hq);
+  const int u = static_cast<int>(idx % hq) * 4;
+  const long long off = static_cast<long long>(r) * H + u;
+  float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c_prev != nullptr) cp = *reinterpret_cast<const float4*>(c_prev + off);
+  if (t >= seq_len[r]) {
+    *reinterpret_cast<float4*>(c_out + off) = cp;
+    uint2 hp = make_uint2(0u, 0u);
+    if (h_prev != nullptr) hp = *reinterpret_cast<const uint2*>(h_prev + off);
+    *reinterpret_cast<uint2*>(h_out + off) = hp;
+    return;
+  }
+  float z[4][4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + g * H + u));
+    z[g][0] = b.x; z[g][1] = b.y; z[g][2] = b.z; z[g][3] = b.w;
+  }
+  for (int s = 0; s < S; ++s) {
+    const float* zp = z_part + s * part_stride + static_cast<long long>(r) * 4 * H + u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 a = *reinterpret_cast<const float4*>(zp + g * H);
+      z[g][0] += a.x; z[g][1] += a.y; z[g][2] += a.z; z[g][3] += a.w;
+    }
+  }
+  const float cpa[4] = {cp.x, cp.y, cp.z, cp.w};
+  float gi[4], gj[4], gf[4], go[4], cn[4], hn[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    gi[k] = sigm_(z[0][k]);
+    gj[k] = tanh_(z[1][k]);
+    gf[k] = sigm_(z[2][k] + 1.0f);
+    go[k] = sigm_(z[3][k]);
+    cn[k] = cpa[k] * gf[k] + gi[k] * gj[k];
+    hn[k] = tanh_(cn[k]) * go[k];
+  }
+  *reinterpret_cast<float4*>(c_out + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  *reinterpret_cast<uint2*>(h_out + off) = pack4_bf16(hn[0], hn[1], hn[2], hn[3]);
+  if (gates != nullptr) {
+    __nv_bfloat16* gp = gates + static_cast<long long>(r) * 4 * H + u;
+    *reinterpret_cast<uint2*>(gp + 0 * H) = pack4_bf16(gi[0], gi[1], gi[2], gi[3]);
+    *reinterpret_cast<uint2*>(gp + 1 * H) = pack4_bf16(gj[0], gj[1], gj[2], gj[3]);
+    *reinterpret_cast<uint2*>(gp + 2 * H) = pack4_bf16(gf[0], gf[1], gf[2], gf[3]);
+    *reinterpret_cast<uint2*>(gp + 3 * H) = pack4_bf16(go[0], go[1], go[2], go[3]);
+  }
+}
+
+// BasicLSTMCell backward at step t: dh = sum_s dh_part[s] (= dz_{t+1} Wh^T) + dh_ext + pass-through;
+// gate gradients dz_t (bf16), carried dc, masked pass-through.  Thread = (row, 4 units).
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_stride,
+                                     const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_prev,
+                                     const float* __restrict__ dh_ext, long long ld_dh_ext,
+                                     const float* __restrict__ dh_pass_in, long long ld_dh_pass_in,
+                                     const float* __restrict__ dc_in, long long ld_dc_in,
+                                     const int* __restrict__ seq_len, int t, int rows, int H,
+                                     __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dc_out,
+                                     float* __restrict__ dh_pass_out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int hq = H >> 2;
+  if (idx >= static_cast<long long>(rows) * hq) return;
+  const int r = static_cast<int>(idx / hq);
+  const int u = static_cast<int>(idx % hq) * 4;
+  const long long off = static_cast<long long>(r) * H + u;
+  const int len = seq_len[r];
+  const bool live = t < len;
+  float dh[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < S; ++s) {
+    const float4 a = *reinterpret_cast<const float4*>(dh_part + s * part_stride + off);
+    dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
+  }
+  if (dh_ext != nullptr) {
+    const float4 a = *reinterpret_cast<const float4*>(dh_ext + static_cast<long long>(r) * ld_dh_ext + u);
+    dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
+  }
+  if (t + 1 >= len && dh_pass_in != nullptr) {   // row was masked at step t+1 (or t is the last step)
+    const float4 a = *reinterpret_cast<const float4*>(dh_pass_in + static_cast<long long>(r) * ld_dh_pass_in + u);
+    dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
+  }
+  if (dc_in != nullptr) {
+    const float4 a = *reinterpret_cast<const float4*>(dc_in + static_cast<long long>(r) * ld_dc_in + u);
+    dc[0] = a.x; dc[1] = a.y; dc[2] = a.z; dc[3] = a.w;
+  }
+  __nv_bfloat16* zp = dz_out + static_cast<long long>(r) * 4 * H + u;
+  if (!live) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
+    *reinterpret_cast<float4*>(dc_out + off) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+    *reinterpret_cast<float4*>(dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+    return;
+  }
+  const __nv_bfloat16* gp = gates + static_cast<long long>(r) * 4 * H + u;
+  float gi[4], gj[4], gf[4], go[4], cp[4] = {0.f, 0.f, 0.f, 0.f};
+  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 0 * H), gi);
+  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 1 * H), gj);
+  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 2 * H), gf);
+  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 3 * H), go);
+  if (c_prev != nullptr) {
+    const float4 a = *reinterpret_cast<const float4*>(c_prev + off);
+    cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w;
+  }
+  float di[4], dj[4], df[4], dq[4], dco[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float cn = cp[k] * gf[k] + gi[k] * gj[k];
+    const float tc = tanh_(cn);
+    const float dcn = dc[k] + dh[k] * go[k] * (1.f - tc * tc);
+    di[k] = dcn * gj[k] * gi[k] * (1.f - gi[k]);
+    dj[k] = dcn * gi[k] * (1.f - gj[k] * gj[k]);
+    df[k] = dcn * cp[k] * gf[k] * (1.f - gf[k]);
+    dq[k] = dh[k] * tc * go[k] * (1.f - go[k]);
+    dco[k] = dcn * gf[k];
+  }
+  *reinterpret_cast<uint2*>(zp + 0 * H) = pack4_bf16(di[0], di[1], di[2], di[3]);
+  *reinterpret_cast<uint2*>(zp + 1 * H) = pack4_bf16(dj[0], dj[1], dj[2], dj[3]);
+  *reinterpret_cast<uint2*>(zp + 2 * H) = pack4_bf16(df[0], df[1], df[2], df[3]);
+  *reinterpret_cast<uint2*>(zp + 3 * H) = pack4_bf16(dq[0], dq[1], dq[2], dq[3]);
+  *reinterpret_cast<float4*>(dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+}
+
 // f32 [R,C] -> bf16 [R,ld] (columns C..ld-1 zero): bf16 operand copies of weights / activations
 __global__ void cast_bf16_kernel(const float* __restrict__ src, long long R, int C, int ld,
                                  __nv_bfloat16* __restrict__ dst) {
@@ -415,6 +558,30 @@ inline int grid_for(long long n, int block, int cap) {
 }  // namespace
 
 #define EVC_STREAM(s) static_cast<cudaStream_t>(s)
+
+namespace evc {
+int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, const float* bias, const float* c_prev,
+                         const void* h_prev, const int* seq_len, int t, int rows, int H, float* c_out, void* h_out,
+                         void* gates, cudaStream_t stream) {
+  const long long n = static_cast<long long>(rows) * (H / 4);
+  lstm_cell_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      z_part, S, part_stride, bias, c_prev, static_cast<const __nv_bfloat16*>(h_prev), seq_len, t, rows, H, c_out,
+      static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(gates));
+  count_launch();
+  return check_launch("lstm_cell_fwd");
+}
+int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, const void* gates, const float* c_prev,
+                         const float* dh_ext, long long ld_dh_ext, const float* dh_pass_in, long long ld_dh_pass_in,
+                         const float* dc_in, long long ld_dc_in, const int* seq_len, int t, int rows, int H,
+                         void* dz_out, float* dc_out, float* dh_pass_out, cudaStream_t stream) {
+  const long long n = static_cast<long long>(rows) * (H / 4);
+  lstm_cell_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      dh_part, S, part_stride, static_cast<const __nv_bfloat16*>(gates), c_prev, dh_ext, ld_dh_ext, dh_pass_in,
+      ld_dh_pass_in, dc_in, ld_dc_in, seq_len, t, rows, H, static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out);
+  count_launch();
+  return check_launch("lstm_cell_bwd");
+}
+}  // namespace evc
 
 extern "C" int evc_frames_pack(const float* src, int B, int T, int D, const int* frame_idx, int idx_per_batch,
                                int K, int num_chunks, int normalize, void* out_bf16, float* out_f32, void* stream) {

@@ -68,6 +68,10 @@ class HLstmEngine:
         self.G = torch.empty(B, self.ldg, dtype=torch.float32, device=dev)
         self.E = torch.empty(B, self.lde, dtype=torch.float32, device=dev)
         self.pred = torch.empty(B, V, dtype=torch.float32, device=dev)
+        # split-K partial slabs of the recurrence steps (one scratch buffer shared by all cells)
+        ws = max(ops.lstm_workspace_bytes(R1, H, D), ops.lstm_workspace_bytes(R1, H, H),
+                 ops.lstm_workspace_bytes(B, H, S), ops.lstm_workspace_bytes(B, H, H))
+        self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
         if training:
             self.lddg, self.ldde = ops.pad8(self.ldg, 64), ops.pad8(self.lde, 64)
             self.dG = torch.zeros(B, self.lddg, dtype=BF16, device=dev)
@@ -86,7 +90,8 @@ class HLstmEngine:
     def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len):
         p = self.p
         ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
-                         layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates)
+                         layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates,
+                         self.workspace)
 
     def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
                 num_frames: torch.Tensor) -> None:
@@ -133,7 +138,7 @@ class HLstmEngine:
         ld = dfinal.stride(0)
         ops.lstm_seq_bwd(p.shadow[p.kernel(level, cell)], Kx, layer.rows, H, layer.T, seq_len, layer.gates,
                          layer.c_all, dh_ext, dfinal[:, col + H:], ld, dfinal[:, col:], ld,
-                         scratch[0], scratch[1], layer.dz)
+                         scratch[0], scratch[1], layer.dz, self.workspace)
 
     def _cell_wgrad(self, layer: _Layer, level, cell, x2d, Kx):
         """dW = [x | h_prev]^T dz over all steps and rows; db = column sums of dz."""

@@ -80,16 +80,24 @@ def random_sequence_index(u, num_frames, K):
     return idx
 
 
-def lstm_seq_fwd(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_all, gates_all):
+def lstm_workspace_bytes(rows, H, Kx):
+    return int(lib.evc_lstm_workspace_bytes(rows, H, Kx))
+
+
+def lstm_seq_fwd(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_all, gates_all, workspace=None):
     check(lib.evc_lstm_seq_fwd(ptr(x), x_step_stride, Kx, ptr(W), ptr(bias), rows, H, T, ptr(seq_len), ptr(h_all),
-                               ptr(c_all), ptr(gates_all), stream()), "evc_lstm_seq_fwd")
+                               ptr(c_all), ptr(gates_all), ptr(workspace),
+                               workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                               stream()), "evc_lstm_seq_fwd")
 
 
 def lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates_all, c_all, dh_ext_all, dh_final, ld_dh_final, dc_final,
-                 ld_dc_final, dh_pass, dc, dz_all):
+                 ld_dc_final, dh_pass, dc, dz_all, workspace=None):
     check(lib.evc_lstm_seq_bwd(ptr(W), Kx, rows, H, T, ptr(seq_len), ptr(gates_all), ptr(c_all), ptr(dh_ext_all),
                                ptr(dh_final), ld_dh_final, ptr(dc_final), ld_dc_final, ptr(dh_pass), ptr(dc),
-                               ptr(dz_all), stream()), "evc_lstm_seq_bwd")
+                               ptr(dz_all), ptr(workspace),
+                               workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                               stream()), "evc_lstm_seq_bwd")
 
 
 def state_pack(c0, h0, c1, h1, rows, H, out_bf16=None, out_f32=None):

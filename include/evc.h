@@ -76,17 +76,23 @@ int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
  * [(T+1),rows,H] receive the state after every step (slot 0 = initial zero state, not read).
  * gates_all bf16 [T,rows,4H] (nullable) keeps the post-activation gates for the backward pass. */
 int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias, int rows,
-                     int H, int T, const int* seq_len, void* h_all, float* c_all, void* gates_all, void* stream);
+                     int H, int T, const int* seq_len, void* h_all, float* c_all, void* gates_all, void* workspace,
+                     long long workspace_bytes, void* stream);
+/* Scratch needed by evc_lstm_seq_fwd / evc_lstm_seq_bwd for one cell (split-K partial slabs).  With a
+ * workspace, steps with <= 1024 rows (RNN_L2, the student) run as a split-K GEMM over all SMs + a
+ * full-occupancy cell kernel; without one (NULL) every step uses the fused-epilogue kernel. */
+long long evc_lstm_workspace_bytes(int rows, int H, int Kx);
 
 /* Backward twin: for t = T-1..0 one fused kernel computing dz_{t+1} * Wh^T on tcgen05 and, in the
  * epilogue, the gate gradients dz_t (bf16 [T,rows,4H]) with the sequence_length mask.
  * dh_ext_all f32 [T,rows,H] (nullable): gradient w.r.t. the cell output at each step (from the cell
  * above).  dh_final/dc_final (nullable, row pitches ld_*): gradient w.r.t. the final state.
- * dh_pass, dc: f32 [rows,H] scratch. */
+ * dh_pass, dc: f32 [rows,H] scratch.  With a workspace the recurrent dgrad runs as a (split-K) GEMM
+ * + a full-occupancy cell kernel (measured faster); NULL selects the fused-epilogue kernel. */
 int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len, const void* gates_all,
                      const float* c_all, const float* dh_ext_all, const float* dh_final, long long ld_dh_final,
                      const float* dc_final, long long ld_dc_final, float* dh_pass, float* dc, void* dz_all,
-                     void* stream);
+                     void* workspace, long long workspace_bytes, void* stream);
 
 /* final MultiRNNCell state [c0|h0|c1|h1] (state_is_tuple=False; frame_level_models.py:252,257). */
 int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,

@@ -63,11 +63,14 @@ def _lstm_ref(x, W, b, seq_len, T, H, dtype=torch.float64):
     return c, h, torch.stack(hs)
 
 
-@pytest.mark.parametrize("rows,Kx,H,T", [(200, 128, 128, 5), (256, 1152, 1024, 3)])
-def test_lstm_seq_fwd_bwd(rows, Kx, H, T):
+@pytest.mark.parametrize("use_ws", [False, True])
+@pytest.mark.parametrize("rows,Kx,H,T", [(200, 128, 128, 5), (256, 1152, 1024, 3), (1300, 256, 128, 4)])
+def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
+    """use_ws=False: fused-epilogue kernels; True: split-K GEMM + cell kernels (fwd only for <=1024 rows)."""
     from efficientvideoclassification_youtube8m_b200 import ops
     torch.manual_seed(0)
     dev = "cuda"
+    ws = torch.empty(ops.lstm_workspace_bytes(rows, H, Kx), dtype=torch.uint8, device=dev) if use_ws else None
     x = (torch.randn(T, rows, Kx, device=dev) * 0.5).to(torch.bfloat16)
     W = (torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)).to(torch.bfloat16)
     b = torch.randn(4 * H, device=dev) * 0.1
@@ -76,7 +79,7 @@ def test_lstm_seq_fwd_bwd(rows, Kx, H, T):
     h_all = torch.zeros(T + 1, rows, H, dtype=torch.bfloat16, device=dev)
     c_all = torch.zeros(T + 1, rows, H, device=dev)
     gates = torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev)
-    ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates)
+    ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, ws)
     torch.cuda.synchronize()
 
     xd = x.double().requires_grad_(True)
@@ -99,7 +102,7 @@ def test_lstm_seq_fwd_bwd(rows, Kx, H, T):
     dh_pass = torch.zeros(rows, H, device=dev)
     dc = torch.zeros(rows, H, device=dev)
     dh_ext_masked = torch.where(live_all, dh_ext, torch.zeros_like(dh_ext)).contiguous()
-    ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc, dz)
+    ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc, dz, ws)
     # wgrad: dW = [x | h_prev]^T dz ; dX = dz Wx^T ; db = colsum dz
     dW = torch.zeros(Kx + H, 4 * H, device=dev)
     R = T * rows
