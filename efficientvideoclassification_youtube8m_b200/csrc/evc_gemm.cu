@@ -52,6 +52,7 @@ static int make_tmap_b(CUtensorMap* m, const void* p, int b_mn, long long ld, in
 }
 
 constexpr int kCluster = 2;   // CTAs per cluster sharing a multicast B tile
+static int g_debug = 0;       // profiling experiments only (evc_debug_set)
 
 template <int A_MN, int B_MN, int BN, int EPI, int CS>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& args,
@@ -110,6 +111,7 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   g.split_k = ceil_div(g.kb_total, g.kb_per_split);
   g.C = C; g.ldc = ldc; g.c_bf16 = c_bf16; g.bias = bias;
   g.split_stride = split_stride;
+  g.debug = g_debug;
   g.atomic_add = (split_stride == 0 && (g.split_k > 1 || accumulate)) ? 1 : 0;
   if (splits_out) *splits_out = g.split_k;
   CUtensorMap ta, ta2, tb;
@@ -120,7 +122,14 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
     rc = make_tmap_a(&ta2, A2, a_mn, K - K1, M, K - K1);
     if (rc) return rc;
   }
-  const int cs = (g.tiles_m >= 2) ? kCluster : 1;
+  int cs = (g.tiles_m >= 2) ? kCluster : 1;
+  if (cs > 1) {   // pairing must not add a round over the SMs (odd tile counts pad to a dummy tile)
+    const long long w1 = static_cast<long long>(g.tiles_m) * g.tiles_n * g.split_k;
+    const long long w2 = static_cast<long long>(ceil_div(g.tiles_m, cs)) * g.tiles_n * g.split_k;
+    const long long r1 = (w1 + num_sms() - 1) / num_sms();
+    const long long r2 = (w2 + num_sms() / cs - 1) / (num_sms() / cs);
+    if (r2 > r1) cs = 1;
+  }
   rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn, cs);
   if (rc) return rc;
 #define EVC_DISPATCH(AM, BMN)                                                                    \
@@ -143,7 +152,6 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
 
 using namespace evc;
 
-static int g_debug = 0;
 extern "C" int evc_debug_set(int flags) { g_debug = flags; return 0; }
 
 extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
@@ -154,18 +162,24 @@ extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
 }
 
 // ------------------------------------------------------------------ BasicLSTM layer, forward over T steps
-// split-K factor for a recurrence step whose output has `tiles` tiles: fill the SMs, keep >= 8 k blocks
+// split-K factor for a GEMM with `tiles` output tiles and kb_total 64-deep k blocks: minimise
+// (rounds over the SMs) x (k blocks per split) + a per-round prologue/epilogue cost of ~4 k blocks.
 static int pick_split(int tiles, int kb_total) {
-  int s = num_sms() / (tiles > 0 ? tiles : 1);
-  if (s > 8) s = 8;
-  while (s > 1 && kb_total / s < 8) --s;
-  return s < 1 ? 1 : s;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= 16; ++s) {
+    if (s > 1 && kb_total / s < 4) break;
+    const long long rounds = (static_cast<long long>(tiles) * s + num_sms() - 1) / num_sms();
+    const long long cost = rounds * ((kb_total + s - 1) / s + 4);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
   // forward small-row path: S x rows x 4H f32 ; backward: S x rows x H f32
   const int sf = (rows <= 1024) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
-  const int sb = pick_split(ceil_div(rows, BM) * (H / 128), 4 * H / BK);
+  const int sb = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
   const long long f = static_cast<long long>(sf) * rows * 4 * H * 4;
   const long long b = static_cast<long long>(sb) * rows * H * 4;
   return (f > b ? f : b) + 256;
@@ -255,7 +269,7 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     // kernel.  Measured faster than the fused epilogue at every row count: the cell backward moves
     // 36 B per element, which 4 epilogue warps per SM cannot keep in flight behind a 4096-deep GEMM.
     float* part = static_cast<float*>(workspace);
-    const int want = pick_split(ceil_div(rows, BM) * (H / 128), 4 * H / BK);
+    const int want = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
     if (static_cast<long long>(want) * RH * 4 > workspace_bytes)
       return set_error(EVC_ERR_ARG, "lstm_seq_bwd: workspace too small (evc_lstm_workspace_bytes)");
     for (int t = T - 1; t >= 0; --t) {
@@ -263,7 +277,7 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
       int splits = 0;
       if (!last) {
         int rc = gemm_store(zb + (t + 1) * RH * 4, 0, 4LL * H, wh, 0, 4LL * H, rows, H, 4 * H, part, 0, H, nullptr,
-                            want, 0, stream, 128, RH, &splits);
+                            want, 0, stream, 256, RH, &splits);
         if (rc) return rc;
       }
       int rc = launch_lstm_cell_bwd(part, splits, RH, gb + t * RH * 4, (t == 0) ? nullptr : c_all + t * RH,

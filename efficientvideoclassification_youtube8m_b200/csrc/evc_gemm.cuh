@@ -387,6 +387,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           tmem_ld_wait();
           const int col0 = n_blk * BN + c0;
           if (col0 >= args.N || nrows <= 0) continue;   // warp-uniform
+          if (args.debug & 64) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -415,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             if (!args.atomic_add && vec) {
               stage_put_f32(st_f, lane, v);
               __syncwarp();
-              flush_f32(st_f, cp, args.ldc, nrows, lane);
+              if (!(args.debug & 32)) flush_f32(st_f, cp, args.ldc, nrows, lane);
               __syncwarp();
             } else if (args.atomic_add) {
               stage_put_f32(st_f, lane, v);
