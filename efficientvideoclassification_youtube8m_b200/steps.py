@@ -57,22 +57,42 @@ class _Base:
         self.frame_idx = torch.tensor(idx, dtype=torch.int32, device=self.device)
         self.nf_student = torch.zeros(batch_size, dtype=torch.int64, device=self.device)
         self.global_step = 0
-        self._graph = None
+        self._pending = []
 
     @staticmethod
     def _world():
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
-    def _allreduce(self, params):
-        """Average the flat gradient buffer over the data-parallel ranks (NCCL AVG over NVLink; the
-        gloo backend of the CPU tests has no AVG and uses SUM / world)."""
+    def _allreduce(self, params, lo: int = 0, hi: Optional[int] = None):
+        """Average (a slice of) the flat gradient buffer over the data-parallel ranks.  With NCCL the
+        collective is asynchronous: it runs on NCCL's stream over NVLink while this rank keeps
+        launching backward kernels, and is waited for in `_finish_allreduce` before the optimizer.
+        (The gloo backend of the CPU tests has no AVG and uses SUM / world.)"""
         n = self._world()
-        if n > 1:
-            if dist.get_backend() == "nccl":
-                dist.all_reduce(params.flat_g, op=dist.ReduceOp.AVG)
+        if n <= 1:
+            return
+        buf = params.flat_g[lo:hi] if (lo or hi is not None) else params.flat_g
+        if dist.get_backend() == "nccl":
+            self._pending.append((params, dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=True)))
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            buf.div_(n)
+
+    def _finish_allreduce(self, params=None):
+        """Wait for the outstanding collectives (of one parameter set, or all)."""
+        keep = []
+        for p, w in self._pending:
+            if params is None or p is params:
+                w.wait()
             else:
-                dist.all_reduce(params.flat_g, op=dist.ReduceOp.SUM)
-                params.flat_g.div_(n)
+                keep.append((p, w))
+        self._pending = keep
+
+    @staticmethod
+    def _moe_offset(params) -> int:
+        """Offset of the classifier tensors in the flat buffers (they follow the 8 LSTM tensors); their
+        gradients (2/3 of the bytes) are final right after classifier_backward."""
+        return params.offsets[params.gates_w]
 
     def _check(self, raw, num_frames, labels):
         if raw.dtype != torch.float32 or raw.dim() != 3 or raw.shape[1] != MAX_FRAMES:
@@ -111,12 +131,19 @@ class TeacherStudentTrainer(_Base):
         s.forward(raw, self.frame_idx, True, self.nf_student)
         # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term
         ops.ce_kl_loss(t.pred, None, labels_u8, 1.0 / B, 0.0, self.rows[0], None, t.dP)
-        t.backward(t.dP)
+        mo_t, mo_s = self._moe_offset(self.teacher), self._moe_offset(self.student)
+        t.classifier_backward(t.dP)
+        self._allreduce(self.teacher, mo_t, None)      # classifier gradients travel during the LSTM backward
+        t.lstm_backward()
+        self._allreduce(self.teacher, 0, mo_t)
         # student loss = 2*L_REP + L_PRED + L_CE + penalty*reg (train.py:359-406); teacher tensors are
         # constants for the student's backward (F9)
         ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
         ops.ce_kl_loss(s.pred, t.pred, labels_u8, 1.0 / B, 1.0, self.rows[1], self.rows[2], s.dP)
-        s.backward(s.dP, dstate_preset=True)
+        s.classifier_backward(s.dP, dstate_preset=True)
+        self._allreduce(self.student, mo_s, None)
+        s.lstm_backward()
+        self._allreduce(self.student, 0, mo_s)
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
         ops.reduce_rows(self.rows[1], 1.0 / B, self.losses[1:2])
         ops.reduce_rows(self.rows[2], 1.0, self.losses[2:3])
@@ -131,9 +158,11 @@ class TeacherStudentTrainer(_Base):
         results with :meth:`fetch`."""
         self._check(model_input_raw, num_frames, labels)
         self.forward_backward(model_input_raw, num_frames, _as_u8(labels))
-        self._allreduce(self.teacher)
-        self._allreduce(self.student)
-        self.apply_gradients()
+        # the teacher's optimizer pass runs while the student's last gradient slice is still on the wire
+        self._finish_allreduce(self.teacher)
+        self.teacher.apply_gradients(self.lr, self.clip, self.penalty)
+        self._finish_allreduce(self.student)
+        self.student.apply_gradients(self.lr, self.clip, self.penalty)
         self.global_step += 2
 
     def fetch(self) -> Dict[str, float]:
@@ -173,9 +202,13 @@ class StudentFinetuneTrainer(_Base):
         ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
         s.forward(model_input_raw, self.frame_idx, True, self.nf_student)
         ops.ce_kl_loss(s.pred, None, _as_u8(labels), 1.0 / B, 0.0, self.rows[0], None, s.dP)
-        s.backward(s.dP)
+        s.classifier_backward(s.dP)
+        mo = self._moe_offset(self.student)
+        self._allreduce(self.student, mo, None)
+        s.lstm_backward()
+        self._allreduce(self.student, 0, mo)
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
-        self._allreduce(self.student)
+        self._finish_allreduce()
         self.student.apply_gradients(self.lr, self.clip, self.penalty)
         self.global_step += 1
 

@@ -25,7 +25,11 @@ def _worker(rank, world, port, out):
     class P:                       # stands in for HLstmParams: the allreduce only touches flat_g
         flat_g = torch.arange(10, dtype=torch.float32) * (rank + 1)
     # gloo has no AVG: the step falls back to SUM / world
-    _Base._allreduce(_Base.__new__(_Base), P)
+    b = _Base.__new__(_Base)
+    b._pending = []
+    _Base._allreduce(b, P, 0, 4)
+    _Base._allreduce(b, P, 4, None)       # the step reduces the flat buffer in two slices
+    b._finish_allreduce()
     want = torch.arange(10, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     ok = torch.allclose(P.flat_g, want)
     gathered = [torch.zeros(10) for _ in range(world)]
