@@ -486,16 +486,33 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
     scale = (ns > 0.f) ? clip * fminf(rsqrtf(ns), 1.0f / clip) : 1.f;
   }
   const float lr = *lr_t;
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  // 4 parameters per thread and iteration (every tensor size and `cols` is a multiple of 4)
+  const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float wi = w[i];
-    const float gi = (g[i] + wd * wi) * scale;
-    float mi = m[i], vi = v[i];
-    mi += (gi - mi) * (1.f - b1);
-    vi += (gi * gi - vi) * (1.f - b2);
-    wi -= lr * mi / (sqrtf(vi) + eps);
-    m[i] = mi; v[i] = vi; w[i] = wi;
-    if (shadow) shadow[(i / cols) * ld_shadow + (i % cols)] = __float2bfloat16(wi);
+  for (long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const long long i = i4 << 2;
+    float4 wv = *reinterpret_cast<const float4*>(w + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float4 mv = *reinterpret_cast<const float4*>(m + i);
+    float4 vv = *reinterpret_cast<const float4*>(v + i);
+    float wa[4] = {wv.x, wv.y, wv.z, wv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+    float ma[4] = {mv.x, mv.y, mv.z, mv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gi = (ga[k] + wd * wa[k]) * scale;
+      ma[k] += (gi - ma[k]) * c1;
+      va[k] += (gi * gi - va[k]) * c2;
+      wa[k] -= lr * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
+    *reinterpret_cast<float4*>(w + i) = make_float4(wa[0], wa[1], wa[2], wa[3]);
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(wa[0], wa[1]), hi = __floats2bfloat162_rn(wa[2], wa[3]);
+      *reinterpret_cast<uint2*>(shadow + (i / cols) * ld_shadow + (i % cols)) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
   }
 }
 
@@ -727,7 +744,11 @@ extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long 
                              float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2,
                              float eps, void* shadow_bf16, int cols, long long ld_shadow, void* stream) {
   if (shadow_bf16 && cols <= 0) return set_error(EVC_ERR_ARG, "clip_adam: cols required with a bf16 copy");
-  clip_adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, EVC_STREAM(stream)>>>(
+  if (n % 4 != 0 || (shadow_bf16 && (cols % 4 != 0 || ld_shadow % 4 != 0)) ||
+      ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15))
+    return set_error(EVC_ERR_ARG, "clip_adam: tensors must be 16-byte aligned with sizes/cols multiple of 4");
+  clip_adam_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(
       w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps,
       static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow);
   count_launch();
