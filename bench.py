@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -198,7 +198,6 @@ def run_ours(args):
     launches_per_step = _lib.launch_count() - n0
     sampler.start()
     ms_step = timed(lambda: tr.step(dx[0], dnf, dlab), args.steps, args.warmup)
-    clocks = sampler.stop()
     losses = tr.fetch()
 
     # ---------------- end to end through the public step API, host buffers (e2e)
@@ -234,6 +233,7 @@ def run_ours(args):
         state["i"] += 1
 
     ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
+    clocks = sampler.stop()          # sampled over both timed regions (device-resident and e2e)
     h2d = host_x[0].numel() * 4 + host_nf.numel() * 4 + host_lab.numel()
     d2h = out_host.numel() * 4 + topk_host.numel() * 4
 

@@ -25,16 +25,17 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor [outer][inner] with row pitch `pitch_elems`; box = box_inner x box_outer, 128B swizzle.
 static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
-                     uint32_t box_inner, uint32_t box_outer) {
+                     uint32_t box_inner, uint32_t box_outer, int elem_bytes = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * 2) % 16 != 0)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * elem_bytes) % 16 != 0)
     return set_error(EVC_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint64_t strides[1] = {pitch_elems * elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
@@ -55,8 +56,8 @@ constexpr int kCluster = 2;   // CTAs per cluster sharing a multicast B tile
 static int g_debug = 0;       // profiling experiments only (evc_debug_set)
 
 template <int A_MN, int B_MN, int BN, int EPI, int CS>
-static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& args,
-                  cudaStream_t stream) {
+static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c,
+                  const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, CS>;
   static bool configured = false;
@@ -82,7 +83,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, c, args);
   count_launch();
   if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(gemm_kernel)");
   return check_launch("gemm_kernel");
@@ -132,13 +133,27 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   }
   rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn, cs);
   if (rc) return rc;
+  // C through TMA bulk stores when its layout allows (16-byte aligned rows) and no atomics are needed
+  CUtensorMap tc = ta;
+  const int eb = c_bf16 ? 2 : 4;
+  // (partial slabs are stacked along the row coordinate of one tensor map: a box must not cross a slab)
+  const bool slab_rows_ok = split_stride == 0 || (split_stride % ldc == 0 && M % 32 == 0);
+  if (!g.atomic_add && !(g_debug & 128) && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * eb) % 16 == 0 &&
+      slab_rows_ok) {
+    const long long slab_rows = split_stride ? split_stride / ldc : 0;
+    const long long total_rows = split_stride ? slab_rows * (g.split_k - 1) + M : M;
+    rc = make_tmap(&tc, C, N, total_rows, ldc, c_bf16 ? 64 : 32, 32, eb);
+    if (rc) return rc;
+    g.tma_store = 1;
+    g.split_rows = static_cast<int>(slab_rows);
+  }
 #define EVC_DISPATCH(AM, BMN)                                                                    \
   if (a_mn == AM && b_mn == BMN) {                                                                \
     if (cs == 1)                                                                                  \
-      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta2, tb, g, stream)               \
-                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta2, tb, g, stream);              \
-    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta2, tb, g, stream)          \
-                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta2, tb, g, stream);         \
+      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream)           \
+                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream);          \
+    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream)      \
+                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream);     \
   }
   EVC_DISPATCH(0, 0)
   EVC_DISPATCH(0, 1)
@@ -244,8 +259,8 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
     g.c_out = c_all + (t + 1) * RH;
     g.h_out = hb + (t + 1) * RH;
     g.gates = gb ? gb + t * RH * 4 : nullptr;
-    rc = (cs == 1) ? launch<0, 1, 256, EPI_LSTM_FWD, 1>(ta1, ta2, tb, g, stream)
-                   : launch<0, 1, 256, EPI_LSTM_FWD, kCluster>(ta1, ta2, tb, g, stream);
+    rc = (cs == 1) ? launch<0, 1, 256, EPI_LSTM_FWD, 1>(ta1, ta2, tb, tb, g, stream)
+                   : launch<0, 1, 256, EPI_LSTM_FWD, kCluster>(ta1, ta2, tb, tb, g, stream);
     if (rc) return rc;
   }
   return EVC_OK;
@@ -318,8 +333,8 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     g.dh_pass_out = dh_pass;
     g.dc_out = dc;
     g.dz_out = zb + t * RH * 4;
-    rc = (cs == 1) ? launch<0, 0, 128, EPI_LSTM_BWD, 1>(ta, ta, tb, g, stream)
-                   : launch<0, 0, 128, EPI_LSTM_BWD, kCluster>(ta, ta, tb, g, stream);
+    rc = (cs == 1) ? launch<0, 0, 128, EPI_LSTM_BWD, 1>(ta, ta, tb, tb, g, stream)
+                   : launch<0, 0, 128, EPI_LSTM_BWD, kCluster>(ta, ta, tb, tb, g, stream);
     if (rc) return rc;
   }
   return EVC_OK;

@@ -40,6 +40,8 @@ struct GemmArgs {
   int c_bf16;          // 0: float, 1: bf16
   int atomic_add;      // 1: red.add.f32 into C (split-K or accumulate)
   long long split_stride;  // != 0: split ks stores its partial product at C + ks*split_stride (no atomics)
+  int tma_store;       // 1: C is written with TMA bulk stores through tensor map tmC (row offset ks*split_rows)
+  int split_rows;      // rows between partial slabs in tmC's row coordinate
   const float* bias;   // [N] or null
   // ---- EPI_LSTM_FWD / BWD (row r, hidden unit u; H = N/4 for fwd, N for bwd)
   int H;
@@ -67,10 +69,10 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int ACC_STAGES = 2;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  // per epilogue warp: accumulator staging, 4 blocks of 32 rows x 16 words (pitch 17) for the LSTM
-  // forward (one per gate) or one block of 32 x 32 (pitch 33) for the backward
-  static constexpr int EPI_STAGE_WORDS = 4 * 32 * 17;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + EPI_WARPS * EPI_STAGE_WORDS * 4;
+  // per epilogue warp 8 KB (1024-byte aligned): two 32x32-word TMA store boxes (plain GEMM), or the
+  // accumulator transposition area of the LSTM epilogues (4 XOR-swizzled 32x16 blocks / one 32x33 block)
+  static constexpr int EPI_STAGE_WORDS = 2048;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_WORDS * 4 + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -232,18 +234,18 @@ __device__ __forceinline__ void flush_bf16(const float* st, __nv_bfloat16* g, lo
 template <int A_MN, int B_MN, int BN, int EPI, int CS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + EPI_WARPS * Cfg::EPI_STAGE_WORDS * 4);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + Cfg::ACC_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::ACC_STAGES);
-  float* epi_stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -380,6 +382,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       if constexpr (EPI == EPI_STORE) {
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
+        if (args.tma_store) {
+          // TMEM -> registers -> swizzled 32x(128 B) box in shared memory -> one TMA bulk store per box.
+          // The LSU sees only conflict-free 16-byte shared stores; clipping of M/N tails is done by TMA.
+          constexpr int CW = 32;                      // f32 columns per box (bf16: 64 columns, same 128 B)
+          const int cols_per_box = args.c_bf16 ? 2 * CW : CW;
+          int buf = 0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += cols_per_box) {
+            const int col0 = n_blk * BN + c0;
+            uint32_t r[32];
+            if (args.c_bf16) {
+              uint32_t lo[32], hi[32];
+              tmem_ld32(taddr + c0, lo);
+              tmem_ld32(taddr + c0 + 32, hi);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a0 = __uint_as_float(lo[2 * j]), a1 = __uint_as_float(lo[2 * j + 1]);
+                float b0 = __uint_as_float(hi[2 * j]), b1 = __uint_as_float(hi[2 * j + 1]);
+                if (args.bias != nullptr && ks == 0) {
+                  a0 += (col0 + 2 * j < args.N) ? __ldg(args.bias + col0 + 2 * j) : 0.f;
+                  a1 += (col0 + 2 * j + 1 < args.N) ? __ldg(args.bias + col0 + 2 * j + 1) : 0.f;
+                  b0 += (col0 + 32 + 2 * j < args.N) ? __ldg(args.bias + col0 + 32 + 2 * j) : 0.f;
+                  b1 += (col0 + 33 + 2 * j < args.N) ? __ldg(args.bias + col0 + 33 + 2 * j) : 0.f;
+                }
+                __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1), pb = __floats2bfloat162_rn(b0, b1);
+                r[j] = *reinterpret_cast<uint32_t*>(&pa);
+                r[16 + j] = *reinterpret_cast<uint32_t*>(&pb);
+              }
+            } else {
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+              if (args.bias != nullptr && ks == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < args.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(args.bias + col0 + j));
+              }
+            }
+            if (col0 >= args.N || nrows <= 0) continue;        // warp-uniform: nothing to store
+            // the box that used this buffer two iterations ago must have been read by the TMA engine
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            uint8_t* box = reinterpret_cast<uint8_t*>(stage) + buf * 4096;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {                      // row = lane, 16-byte chunk c, 128B swizzle
+              const uint32_t sw = static_cast<uint32_t>(c ^ (lane & 7));
+              *reinterpret_cast<uint4*>(box + lane * 128 + sw * 16) =
+                  make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, box, col0, ks * args.split_rows + row0);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+          if (lane == 0) tma_store_wait_read<0>();              // staging is free again for the next tile
+          __syncwarp();
+        } else
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
           uint32_t r[16];
@@ -460,11 +522,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tmem_ld_wait();
             if (args.debug == 1) continue;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              stage[0 * 544 + lane * 17 + j] = __uint_as_float(ri[j]);
-              stage[1 * 544 + lane * 17 + j] = __uint_as_float(rj[j]);
-              stage[2 * 544 + lane * 17 + j] = __uint_as_float(rf[j]);
-              stage[3 * 544 + lane * 17 + j] = __uint_as_float(ro[j]);
+            for (int j = 0; j < 16; ++j) {                   // [gate][row][col ^ (row & 15)]
+              const int sj = lane * 16 + (j ^ (lane & 15));
+              stage[0 * 512 + sj] = __uint_as_float(ri[j]);
+              stage[1 * 512 + sj] = __uint_as_float(rj[j]);
+              stage[2 * 512 + sj] = __uint_as_float(rf[j]);
+              stage[3 * 512 + sj] = __uint_as_float(ro[j]);
             }
           }
           __syncwarp();
@@ -490,15 +553,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           for (int i = 0; i < 4; ++i) {
             const int rl = pr + 8 * i;
             const int r = row0 + rl;
-            const float* sp = stage + rl * 17 + pc;
+            const float* sp = stage + rl * 16;
             const float cp[4] = {cpv[i].x, cpv[i].y, cpv[i].z, cpv[i].w};
             float cn[4], hn[4], g4[4][4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              g4[0][k] = sigmoid_f(sp[0 * 544 + k] + bia[0][k]);
-              g4[1][k] = tanh_f(sp[1 * 544 + k] + bia[1][k]);
-              g4[2][k] = sigmoid_f(sp[2 * 544 + k] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
-              g4[3][k] = sigmoid_f(sp[3 * 544 + k] + bia[3][k]);
+              const int sk = (pc + k) ^ (rl & 15);
+              g4[0][k] = sigmoid_f(sp[0 * 512 + sk] + bia[0][k]);
+              g4[1][k] = tanh_f(sp[1 * 512 + sk] + bia[1][k]);
+              g4[2][k] = sigmoid_f(sp[2 * 512 + sk] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
+              g4[3][k] = sigmoid_f(sp[3 * 512 + sk] + bia[3][k]);
               cn[k] = cp[k] * g4[2][k] + g4[0][k] * g4[1][k];
               hn[k] = tanh_f(cn[k]) * g4[3][k];
             }
