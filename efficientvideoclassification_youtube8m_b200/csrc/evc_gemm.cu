@@ -113,6 +113,8 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   g.C = C; g.ldc = ldc; g.c_bf16 = c_bf16; g.bias = bias;
   g.split_stride = split_stride;
   g.debug = g_debug;
+  // A too large for the L2 and several N tiles: walk N first so that each A tile is fetched from HBM once
+  g.n_fastest = (static_cast<long long>(M) * K * 2 > (64LL << 20) && g.tiles_n > 1) ? 1 : 0;
   g.atomic_add = (split_stride == 0 && (g.split_k > 1 || accumulate)) ? 1 : 0;
   if (splits_out) *splits_out = g.split_k;
   CUtensorMap ta, ta2, tb;

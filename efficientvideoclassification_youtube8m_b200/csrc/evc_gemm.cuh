@@ -40,6 +40,7 @@ struct GemmArgs {
   int c_bf16;          // 0: float, 1: bf16
   int atomic_add;      // 1: red.add.f32 into C (split-K or accumulate)
   long long split_stride;  // != 0: split ks stores its partial product at C + ks*split_stride (no atomics)
+  int n_fastest;       // tile order: 1 = consecutive work items walk N first (A tile reused from L2)
   int tma_store;       // 1: C is written with TMA bulk stores through tensor map tmC (row offset ks*split_rows)
   int split_rows;      // rows between partial slabs in tmC's row coordinate
   const float* bias;   // [N] or null
@@ -285,8 +286,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
-        const int m_blk = (w % tiles_mc) * CS + cta_rank;
-        const int n_blk = (w / tiles_mc) % args.tiles_n;
+        const int wt = w % (tiles_mc * args.tiles_n);
+        const int m_blk = (args.n_fastest ? wt / args.tiles_n : wt % tiles_mc) * CS + cta_rank;
+        const int n_blk = args.n_fastest ? wt % args.tiles_n : wt / tiles_mc;
         const int ks = w / (tiles_mc * args.tiles_n);
         const int kb0 = ks * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
@@ -367,8 +369,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     float* st_b0 = stage + STG_BF16;
     int it = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
-      const int m_blk = (w % tiles_mc) * CS + cta_rank;
-      const int n_blk = (w / tiles_mc) % args.tiles_n;
+      const int wt = w % (tiles_mc * args.tiles_n);
+      const int m_blk = (args.n_fastest ? wt / args.tiles_n : wt % tiles_mc) * CS + cta_rank;
+      const int n_blk = args.n_fastest ? wt % args.tiles_n : wt / tiles_mc;
       const int ks = w / (tiles_mc * args.tiles_n);
       const bool has_acc = min(args.kb_total, (ks + 1) * args.kb_per_split) > ks * args.kb_per_split;
       const int as = it & 1;
