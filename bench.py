@@ -251,7 +251,11 @@ def run_ours(args):
     achieved = flops_seq / (ms_seq * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "gemm_kernel<A=K,B=MN,BN=256,EPI_LSTM_FWD> (teacher RNN_L1 cell 0)",
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_kind": peak_kind + " burst bf16",
+            "frac": achieved / peaks["bf16_tflops"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
+            # capture committed as profiles/r01_fwd_kernel_ncu_full_summary.txt (65.2 MB + 36.3 MB); the
+            # algorithmic bytes are 61 MB read (x_t, h, W, c) + 73.5 MB written (c, h, gates), the L2 absorbs part
+            "traffic": 101.5e6, "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst bf16",
             "launches_timed": ell, "avg_launch_ms": ms_seq / ell}
 
     # ---------------- student inference (BASELINE config #2), device resident

@@ -423,7 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                   if (col0 + j < args.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(args.bias + col0 + j));
               }
             }
-            if (col0 >= args.N || nrows <= 0) continue;        // warp-uniform: nothing to store
+            if (col0 >= args.N || nrows <= 0 || (args.debug & 64)) continue;   // warp-uniform: nothing to store
             // the box that used this buffer two iterations ago must have been read by the TMA engine
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
@@ -437,7 +437,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmC, box, col0, ks * args.split_rows + row0);
+              if (args.debug & 16) tma_store_2d(&tmC, box, col0, ks * args.split_rows + row0);
+              else if (!(args.debug & 32))   // streamed output must not evict the L2-resident operands
+                tma_store_2d_hint(&tmC, box, col0, ks * args.split_rows + row0, kL2EvictFirst);
               tma_store_commit();
             }
             buf ^= 1;
