@@ -16,6 +16,7 @@ SIGNATURES = {
     "evc_last_error": [],
     "evc_launch_count": [],
     "evc_frames_pack": [P, I, I, I, P, I, I, I, I, P, P, P],
+    "evc_frames_pack_u8": [P, P, I, I, I, P, I, I, I, I, P, P, P],
     "evc_num_frames_student": [P, I, I, I, P, P],
     "evc_lstm_lengths": [P, I, I, I, I, P, P, P],
     "evc_random_frame_index": [P, P, I, I, P, P],

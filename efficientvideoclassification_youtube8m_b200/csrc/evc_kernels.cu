@@ -77,6 +77,59 @@ __global__ void frames_pack_kernel(const float* __restrict__ src, int B, int T, 
   }
 }
 
+// Same, reading the uint8 features as the YT8M tfrecords store them: readers.py:160-172 decodes the
+// bytes, utils.Dequantize (utils.py:9-25, max 2 / min -2) maps q -> q*(4/255) + (4/512 - 2) in
+// float32, and resize_axis zero-pads frames >= num_frames.  Keeping the features uint8 up to this
+// kernel moves 4x fewer bytes over PCIe / HBM (SURVEY 8f "next #1").
+__global__ void frames_pack_u8_kernel(const uint8_t* __restrict__ src, const int* __restrict__ num_frames, int B,
+                                      int T, int D, const int* __restrict__ frame_idx, int idx_per_batch, int K,
+                                      int C, int normalize, __nv_bfloat16* __restrict__ out_bf16,
+                                      float* __restrict__ out_f32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  const int b = warp / K, k = warp % K;
+  const int f = frame_idx ? (idx_per_batch ? frame_idx[b * K + k] : frame_idx[k]) : k;
+  const bool padded = f >= num_frames[b];
+  const uchar4* s = reinterpret_cast<const uchar4*>(src + (static_cast<long long>(b) * T + f) * D);
+  const int n4 = D >> 2;
+  const float scalar = 4.0f / 255.0f, bias = 4.0f / 512.0f - 2.0f;
+  float scale = 1.f;
+  if (normalize && !padded) {
+    float ss = 0.f;
+    for (int i = lane; i < n4; i += 32) {
+      const uchar4 q = __ldg(s + i);
+      const float x0 = __fadd_rn(__fmul_rn(q.x, scalar), bias), x1 = __fadd_rn(__fmul_rn(q.y, scalar), bias);
+      const float x2 = __fadd_rn(__fmul_rn(q.z, scalar), bias), x3 = __fadd_rn(__fmul_rn(q.w, scalar), bias);
+      ss += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+    }
+    ss = warp_sum(ss);
+    scale = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+  }
+  const int ell = K / C;
+  const int chunk = k / ell, tt = k % ell;
+  __nv_bfloat16* ob = out_bf16 ? out_bf16 + ((static_cast<long long>(tt) * C + chunk) * B + b) * D : nullptr;
+  float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + (static_cast<long long>(b) * K + k) * D) : nullptr;
+  for (int i = lane; i < n4; i += 32) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!padded) {
+      const uchar4 q = __ldg(s + i);
+      v.x = __fadd_rn(__fmul_rn(q.x, scalar), bias) * scale;
+      v.y = __fadd_rn(__fmul_rn(q.y, scalar), bias) * scale;
+      v.z = __fadd_rn(__fmul_rn(q.z, scalar), bias) * scale;
+      v.w = __fadd_rn(__fmul_rn(q.w, scalar), bias) * scale;
+    }
+    if (ob) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(ob + 4 * i) = u;
+    }
+    if (of) of[i] = v;
+  }
+}
+
 // train.py:263-264  int64( (n / 300) * int(300/every_n) ) in float64
 __global__ void num_frames_student_kernel(const int* __restrict__ nf, int B, int max_frames, int m,
                                           long long* __restrict__ out) {
@@ -614,6 +667,24 @@ extern "C" int evc_frames_pack(const float* src, int B, int T, int D, const int*
                                                              out_f32);
   count_launch();
   return check_launch("frames_pack");
+}
+
+extern "C" int evc_frames_pack_u8(const unsigned char* src, const int* num_frames, int B, int T, int D,
+                                  const int* frame_idx, int idx_per_batch, int K, int num_chunks, int normalize,
+                                  void* out_bf16, float* out_f32, void* stream) {
+  if (B <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "frames_pack_u8: empty batch");
+  if (D % 4 != 0) return set_error(EVC_ERR_ARG, "frames_pack_u8: feature size must be a multiple of 4");
+  if (num_frames == nullptr) return set_error(EVC_ERR_ARG, "frames_pack_u8: num_frames required (zero padding)");
+  if (num_chunks <= 0 || K % num_chunks != 0)
+    return set_error(EVC_ERR_ARG, "frames_pack_u8: number of frames must split evenly into chunks (tf.split)");
+  const long long warps = static_cast<long long>(B) * K;
+  const int block = 256;
+  const int grid = static_cast<int>((warps * 32 + block - 1) / block);
+  frames_pack_u8_kernel<<<grid, block, 0, EVC_STREAM(stream)>>>(src, num_frames, B, T, D, frame_idx, idx_per_batch, K,
+                                                                num_chunks, normalize,
+                                                                static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  count_launch();
+  return check_launch("frames_pack_u8");
 }
 
 extern "C" int evc_num_frames_student(const int* num_frames, int B, int max_frames, int every_n, long long* out,

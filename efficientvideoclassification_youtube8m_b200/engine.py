@@ -94,21 +94,28 @@ class HLstmEngine:
                          self.workspace)
 
     def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
-                num_frames: torch.Tensor) -> None:
-        """src f32 [B, T_src, D]; frame_idx int32 [K] / [B,K] / None; num_frames int32|int64 [B]
-        (already the *sampled* count for the student).  Fills self.state and self.pred."""
-        self.forward_lstm(src, frame_idx, normalize, num_frames)
+                num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None) -> None:
+        """src f32 (or uint8, quantised) [B, T_src, D]; frame_idx int32 [K] / [B,K] / None; num_frames
+        int32|int64 [B] (already the *sampled* count for the student); raw_num_frames int32 [B] is the
+        unsampled count (uint8 sources only).  Fills self.state and self.pred."""
+        self.forward_lstm(src, frame_idx, normalize, num_frames, raw_num_frames)
         self.classifier_forward()
 
     def forward_lstm(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
-                     num_frames: torch.Tensor) -> None:
+                     num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None) -> None:
         """Both LSTM levels: fills self.state (f32) and self.state_bf16."""
         cfg = self.cfg
         H, D, S = cfg.lstm_cells, cfg.feature_size, cfg.state_size
         B, R1, ell, C = self.B, self.R1, self.ell, self.C
         if src.shape[0] != B or src.shape[2] != D:
             raise ValueError(f"model_input shape {tuple(src.shape)} does not match the plan [{B},*,{D}]")
-        ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x)
+        if src.dtype == torch.uint8:
+            # quantised tfrecord features: Dequantize + zero padding fused into the pack kernel
+            if raw_num_frames is None:
+                raise ValueError("uint8 features need the unsampled num_frames (int32) for zero padding")
+            ops.frames_pack_u8(src, raw_num_frames, frame_idx, self.K, C, normalize, out_bf16=self.x)
+        else:
+            ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x)
         ops.lstm_lengths(num_frames, C, ell, self.len_l1, self.len_l2)
         a, b = self.l1
         self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1)

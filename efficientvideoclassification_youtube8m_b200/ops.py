@@ -42,6 +42,16 @@ def frames_pack(src, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32
                               ptr(out_bf16), ptr(out_f32), stream()), "evc_frames_pack")
 
 
+def frames_pack_u8(src_u8, num_frames, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None):
+    """frames_pack on the quantised (uint8) features: Dequantize + zero padding fused in."""
+    _cuda(src_u8, num_frames, frame_idx, out_bf16, out_f32)
+    assert src_u8.dtype == torch.uint8 and num_frames.dtype == torch.int32
+    B, T, D = src_u8.shape
+    per_batch = int(frame_idx is not None and frame_idx.dim() == 2)
+    check(lib.evc_frames_pack_u8(ptr(src_u8), ptr(num_frames), B, T, D, ptr(frame_idx), per_batch, K, num_chunks,
+                                 int(normalize), ptr(out_bf16), ptr(out_f32), stream()), "evc_frames_pack_u8")
+
+
 def num_frames_student(num_frames, every_n, max_frames=300, out=None):
     _cuda(num_frames)
     assert num_frames.dtype == torch.int32

@@ -154,6 +154,24 @@ class HLstmParams:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {n: self.w[n].detach().clone() for n in self.names}
 
+    def save(self, path: str) -> None:
+        """name -> array map of this scope's variables (`.npz`; keys are the TF checkpoint names)."""
+        np.savez(path, **{n: self.w[n].detach().cpu().numpy() for n in self.names})
+
+    def load(self, path: str, from_scope: Optional[str] = None) -> None:
+        """Load a name -> array map.  `from_scope` renames `<from_scope>/...` keys to this scope: with
+        from_scope="model_student" into scope "model_student" it is the restore of
+        train_convert_model.py:496-517; any other pair re-homes a checkpoint (e.g. student init from
+        the teacher)."""
+        with np.load(path) as z:
+            sd = {}
+            for k in z.files:
+                name = k
+                if from_scope is not None and k.startswith(from_scope + "/"):
+                    name = self.scope + k[len(from_scope):]
+                sd[name] = z[k]
+        self.load_state_dict({n: sd[n] for n in self.names if n in sd}, strict=True)
+
     def refresh_shadows(self) -> None:
         for n, s in self.shadow.items():
             rows, cols = self.shapes[n]

@@ -95,8 +95,8 @@ class _Base:
         return params.offsets[params.gates_w]
 
     def _check(self, raw, num_frames, labels):
-        if raw.dtype != torch.float32 or raw.dim() != 3 or raw.shape[1] != MAX_FRAMES:
-            raise ValueError("model_input_raw must be f32 [B, 300, feature_size]")
+        if raw.dtype not in (torch.float32, torch.uint8) or raw.dim() != 3 or raw.shape[1] != MAX_FRAMES:
+            raise ValueError("model_input_raw must be f32 (dequantised) or uint8 (quantised) [B, 300, feature_size]")
         if num_frames.dtype != torch.int32:
             raise TypeError("num_frames must be int32 (readers.py: tf.minimum(..., max_frames))")
         if labels is not None and tuple(labels.shape) != (raw.shape[0], self.cfg.vocab_size):
@@ -125,10 +125,10 @@ class TeacherStudentTrainer(_Base):
         B = self.B
         t, s = self.t_eng, self.s_eng
         # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
-        t.forward(raw, None, True, num_frames)
+        t.forward(raw, None, True, num_frames, num_frames)
         # student: every_n-th frame, float64 length rule (train.py:262-272,349-357)
         ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(raw, self.frame_idx, True, self.nf_student)
+        s.forward(raw, self.frame_idx, True, self.nf_student, num_frames)
         # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term
         ops.ce_kl_loss(t.pred, None, labels_u8, 1.0 / B, 0.0, self.rows[0], None, t.dP)
         mo_t, mo_s = self._moe_offset(self.teacher), self._moe_offset(self.student)
@@ -200,7 +200,7 @@ class StudentFinetuneTrainer(_Base):
         self._check(model_input_raw, num_frames, labels)
         B, s = self.B, self.s_eng
         ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(model_input_raw, self.frame_idx, True, self.nf_student)
+        s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames)
         ops.ce_kl_loss(s.pred, None, _as_u8(labels), 1.0 / B, 0.0, self.rows[0], None, s.dP)
         s.classifier_backward(s.dP)
         mo = self._moe_offset(self.student)
@@ -239,7 +239,7 @@ class StudentEvaluator(_Base):
         self._check(model_input_raw, num_frames, labels)
         s = self.s_eng
         ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(model_input_raw, self.frame_idx, True, self.nf_student)
+        s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames)
         lab = _as_u8(labels) if labels is not None else None
         if lab is not None:
             ops.ce_kl_loss(s.pred, None, lab, 1.0, 0.0, self.rows, None, None)
@@ -260,7 +260,7 @@ class TeacherEvaluator(_Base):
     def step(self, model_input_raw, num_frames, labels=None):
         self._check(model_input_raw, num_frames, labels)
         t = self.t_eng
-        t.forward(model_input_raw, None, True, num_frames)
+        t.forward(model_input_raw, None, True, num_frames, num_frames)
         lab = _as_u8(labels) if labels is not None else None
         idx, val, tl = ops.topk(t.pred, self.top_k, lab)
         return t.pred, idx, val, tl

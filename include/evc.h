@@ -44,6 +44,13 @@ long long evc_launch_count(void);
 int evc_frames_pack(const float* src, int B, int T, int D, const int* frame_idx, int idx_per_batch, int K,
                     int num_chunks, int normalize, void* out_bf16, float* out_f32, void* stream);
 
+/* Same from the uint8 features of the tfrecords: readers.py:160-172 (decode_raw -> float32) +
+ * utils.Dequantize (utils.py:9-25: q*(4/255) + (4/512 - 2), float32) + zero padding of frames
+ * >= num_frames (readers.py:173 resize_axis), then as evc_frames_pack. */
+int evc_frames_pack_u8(const unsigned char* src, const int* num_frames, int B, int T, int D, const int* frame_idx,
+                       int idx_per_batch, int K, int num_chunks, int normalize, void* out_bf16, float* out_f32,
+                       void* stream);
+
 /* train.py:263-264: int64((num_frames / 300) * int(300/every_n)), evaluated in float64. */
 int evc_num_frames_student(const int* num_frames, int B, int max_frames, int every_n, long long* out,
                            void* stream);

@@ -449,6 +449,21 @@ def gap(predictions: np.ndarray, actuals: np.ndarray, k: int = 20) -> float:
 EDGE_NUM_FRAMES = [1, 5, 6, 9, 10, 14, 15, 16, 29, 30, 150, 299, 300]
 
 
+def dequantize(q: np.ndarray, max_quantized_value=2.0, min_quantized_value=-2.0) -> np.ndarray:
+    """utils.py:9-25 Dequantize in float32: q * (range/255) + (range/512 + min)."""
+    rng_ = max_quantized_value - min_quantized_value
+    scalar = np.float32(rng_ / 255.0)
+    bias = np.float32(rng_ / 512.0 + min_quantized_value)
+    return q.astype(np.float32) * scalar + bias
+
+
+def quantized_batch(batch, seed=1234, num_features=1152, max_frames=MAX_FRAMES):
+    """The uint8 features behind synthetic_batch(stress=False) with the same seed (before Dequantize
+    and zero padding, i.e. what a tfrecord holds)."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(batch, max_frames, num_features), dtype=np.uint8)
+
+
 def synthetic_batch(batch, seed=1234, num_features=1152, vocab_size=4716, full_length=False,
                     max_frames=MAX_FRAMES, stress=False):
     """Dequantised-uint8 features (utils.py:21-25 Dequantize with readers.py:178-179 defaults

@@ -112,3 +112,77 @@ def test_train_steps_loss_curve_small():
             want = float(ref[key])
             assert abs(got[key] - want) <= 0.01 * abs(want) + 1e-4, (it, key, got[key], want)
     assert got["global_step"] == 2 * steps
+
+
+def test_student_finetune_step_cfg4_like():
+    """train_finetune.py step (final_loss = penalty*reg + L_CE) with 4 mixtures (BASELINE config #4 shape
+    family: moe_num_mixtures 4, clip_gradient_norm 1.0), checked against the oracle for 4 steps."""
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import StudentFinetuneTrainer
+    kw = dict(feature_size=128, lstm_cells=256, vocab_size=120, num_mixtures=4)
+    cfg = ModelConfig(**kw)
+    B = 16
+    x, nf, lab = O.synthetic_batch(B, seed=31, num_features=128, vocab_size=120, stress=True)
+    tr = StudentFinetuneTrainer(cfg, batch_size=B, lstm_gain=2.0)
+    S = O.init_params("model_student", 1, dtype=torch.float64, gain=2.0, **kw)
+    opt = O.TFAdam(S)
+    xd, nfd, labd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda(), torch.from_numpy(lab).cuda()
+    for it in range(4):
+        tr.step(xd, nfd, labd)
+        got = tr.fetch()
+        ref = O.student_finetune_step(torch.from_numpy(x).double(), nf, torch.from_numpy(lab), S, opt,
+                                      vocab_size=120, num_mixtures=4)
+        for k in ("l_ce", "student_loss"):
+            want = float(ref[k])
+            assert abs(got[k] - want) <= 0.01 * abs(want) + 1e-4, (it, k, got[k], want)
+        err = (tr.s_eng.pred.cpu().double() - ref["student_predictions"]).abs().max().item()
+        assert err < 1e-3, (it, err)
+    assert got["global_step"] == 4
+
+
+def test_quantized_input_path_matches_dequantized():
+    """uint8 tfrecord features -> Dequantize (utils.py:9-25) + zero padding (readers.py:173) fused into the pack
+    kernel: bit-identical to feeding the dequantised float32 batch."""
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200 import ops
+    from efficientvideoclassification_youtube8m_b200.params import HLstmParams, ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import TeacherEvaluator
+    B, D = 8, 128
+    x, nf, _ = O.synthetic_batch(B, seed=41, num_features=D, vocab_size=50)
+    q = O.quantized_batch(B, seed=41, num_features=D)
+    assert np.array_equal(np.where(np.arange(300)[None, :, None] < nf[:, None, None], O.dequantize(q), 0), x)
+    qd, nfd = torch.from_numpy(q).cuda(), torch.from_numpy(nf).cuda()
+    out = torch.empty(B, 300, D, device="cuda")
+    ops.frames_pack_u8(qd, nfd, None, 300, 1, False, out_f32=out)
+    assert np.array_equal(out.cpu().numpy(), x)                      # Dequantize + padding bit-exact
+    cfg = ModelConfig(feature_size=D, lstm_cells=128, vocab_size=50, num_mixtures=2)
+    ev = TeacherEvaluator(HLstmParams("model", cfg, "cuda", seed=0), B)
+    p_q = ev.step(qd, nfd)[0].clone()
+    p_f = ev.step(torch.from_numpy(x).cuda(), nfd)[0]
+    assert torch.equal(p_q, p_f)
+
+
+def test_checkpoint_roundtrip_and_student_conversion(tmp_path):
+    """name -> array checkpoints keyed by the TF variable names; T+S -> S conversion
+    (train_convert_model.py:496-517 keeps the 11 model_student/* variables)."""
+    from efficientvideoclassification_youtube8m_b200.params import HLstmParams, ModelConfig
+    cfg = ModelConfig(feature_size=128, lstm_cells=128, vocab_size=50, num_mixtures=2)
+    s = HLstmParams("model_student", cfg, "cuda", seed=5)
+    path = str(tmp_path / "student.npz")
+    s.save(path)
+    z = np.load(path)
+    assert sorted(z.files) == sorted(s.names)
+    assert "model_student/RNN_L2/rnn/multi_rnn_cell/cell_1/basic_lstm_cell/bias" in z.files
+    s2 = HLstmParams("model_student", cfg, "cuda", seed=None)
+    s2.load(path)
+    for n in s.names:
+        assert torch.equal(s.w[n], s2.w[n])
+        if n in s.shadow:
+            assert torch.equal(s.shadow[n], s2.shadow[n])
+    t = HLstmParams("model", cfg, "cuda", seed=None)
+    t.load(path, from_scope="model_student")                         # re-home under another scope
+    assert torch.equal(t.w[t.names[0]], s.w[s.names[0]])
+    with pytest.raises(ValueError):
+        HLstmParams("model_student", ModelConfig(feature_size=128, lstm_cells=256, vocab_size=50), "cuda",
+                    seed=None).load(path)
