@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GF_PER_VIDEO_TRAIN = 39.820  # T+S train step, algorithmic GFLOP per video (cfg #1)
+GF_PER_VIDEO_FINETUNE_CFG4 = 16.368  # student fine-tune step at H=2048, M=4 (cfg #4)
 
 
 def _peaks():
@@ -139,7 +140,8 @@ def run_ours(args):
     from oracle import hlstm_oracle as O
     from efficientvideoclassification_youtube8m_b200 import _lib, ops
     from efficientvideoclassification_youtube8m_b200.params import ModelConfig
-    from efficientvideoclassification_youtube8m_b200.steps import StudentEvaluator, TeacherStudentTrainer
+    from efficientvideoclassification_youtube8m_b200.steps import (StudentEvaluator, StudentFinetuneTrainer,
+                                                                   TeacherStudentTrainer)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -149,11 +151,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    cfg = ModelConfig()
+    finetune = args.workload == "finetune_cfg4"
+    cfg = ModelConfig(lstm_cells=2048, num_mixtures=4) if finetune else ModelConfig()
     # Reference hyper-parameters except the learning rate: with the default 1e-3, Adam saturates the
     # MoE on a *repeated* synthetic batch within ~5 steps (p -> 0, KL -> inf; the reference's
     # check_numerics would abort the same way).  The optimizer does identical work at any lr.
-    tr = TeacherStudentTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr)
+    if finetune:   # BASELINE configs[3]: student fine-tune, lstm_cells 2048, 4 mixtures, clip 1.0
+        tr = StudentFinetuneTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr)
+    else:
+        tr = TeacherStudentTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr)
 
     # synthetic batch: two host-pinned copies (double buffering) + a resident one
     x, nf, lab = O.synthetic_batch(B, seed=1234 + rank, full_length=True)
@@ -205,7 +211,7 @@ def run_ours(args):
     main = torch.cuda.current_stream()
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
-    out_host = torch.empty(8, dtype=torch.float32).pin_memory()
+    out_host = torch.empty(tr.losses.numel(), dtype=torch.float32).pin_memory()
     topk_host = torch.empty(B, 20, dtype=torch.int32).pin_memory()
     state = {"i": 0}
 
@@ -237,30 +243,33 @@ def run_ours(args):
     h2d = host_x[0].numel() * 4 + host_nf.numel() * 4 + host_lab.numel()
     d2h = out_host.numel() * 4 + topk_host.numel() * 4
 
-    # ---------------- dominant kernel alone: teacher RNN_L1 cell-0 forward steps (15 launches)
-    t = tr.t_eng
+    # ---------------- dominant kernel alone: RNN_L1 cell-0 forward steps of the teacher (15 launches; the
+    # student's 6 for the fine-tune workload)
+    t = tr.s_eng if finetune else tr.t_eng
+    pset = tr.student if finetune else tr.teacher
     H, D, R1, ell = cfg.lstm_cells, cfg.feature_size, t.R1, t.ell
     lay = t.l1[0]
 
     def l1_fwd():
-        ops.lstm_seq_fwd(t.x, R1 * D, D, tr.teacher.shadow[tr.teacher.kernel(0, 0)],
-                         tr.teacher.w[tr.teacher.bias(0, 0)], R1, H, ell, t.len_l1, lay.h_all, lay.c_all, lay.gates)
+        ops.lstm_seq_fwd(t.x, R1 * D, D, pset.shadow[pset.kernel(0, 0)],
+                         pset.w[pset.bias(0, 0)], R1, H, ell, t.len_l1, lay.h_all, lay.c_all, lay.gates)
     ms_seq = timed(l1_fwd, 5, 3)
     flops_seq = 2.0 * R1 * 4 * H * (D * ell + H * (ell - 1))
     peaks, peak_kind = _peaks()
     achieved = flops_seq / (ms_seq * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "gemm_kernel<A=K,B=MN,BN=256,EPI_LSTM_FWD> (teacher RNN_L1 cell 0)",
+    roof = {"bound": "tensor", "kernel": "gemm_kernel<A=K,B=MN,BN=256,EPI_LSTM_FWD> (%s RNN_L1 cell 0, %d rows)"
+            % ("student" if finetune else "teacher", R1),
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
             # capture committed as profiles/r01_fwd_kernel_ncu_full_summary.txt (65.2 MB + 36.3 MB); the
             # algorithmic bytes are 61 MB read (x_t, h, W, c) + 73.5 MB written (c, h, gates), the L2 absorbs part
-            "traffic": 101.5e6, "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst bf16",
+            "traffic": None if finetune else 101.5e6, "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst bf16",
             "launches_timed": ell, "avg_launch_ms": ms_seq / ell}
 
     # ---------------- student inference (BASELINE config #2), device resident
     infer = None
-    if world == 1 and not args.skip_infer:
+    if world == 1 and not args.skip_infer and not finetune:
         Bi = 1024
         xi, nfi, _ = O.synthetic_batch(Bi, seed=99, full_length=True)
         ev = StudentEvaluator(tr.student, Bi)
@@ -272,17 +281,22 @@ def run_ours(args):
     if rank == 0:
         vps = world * B / (ms_step * 1e-3)
         e2e_vps = world * B / (ms_e2e * 1e-3)
+        gf = GF_PER_VIDEO_FINETUNE_CFG4 if finetune else GF_PER_VIDEO_TRAIN
         line = {
-            "metric": "H-LSTM teacher-student train videos/s", "value": vps, "unit": "videos/s", "n_gpus": world,
+            "metric": "H-LSTM student fine-tune train videos/s" if finetune else
+                      "H-LSTM teacher-student train videos/s", "value": vps, "unit": "videos/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "teacher-student joint train step (run_train.sh defaults; BASELINE configs[0]/[2])",
+            "config": {"workload": "student fine-tune step (run_finetune.sh with lstm_cells 2048, 4 mixtures; "
+                                   "BASELINE configs[3])" if finetune else
+                                   "teacher-student joint train step (run_train.sh defaults; BASELINE configs[0]/[2])",
                        "batch_per_gpu": B, "global_batch": world * B, "frames": 300, "features": 1152,
-                       "every_n": 10, "lstm_cells": 1024, "lstm_layers": 2, "moe_num_mixtures": 2,
+                       "every_n": 10, "lstm_cells": cfg.lstm_cells, "lstm_layers": 2,
+                       "moe_num_mixtures": cfg.num_mixtures,
                        "classes": 4716, "parallelism": f"dp{world}", "base_learning_rate": args.lr,
                        "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2"},
-            "model_tflops": vps * GF_PER_VIDEO_TRAIN / 1e3,
-            "frac_of_sustained_bf16_peak": vps * GF_PER_VIDEO_TRAIN / 1e3 / world / peaks["bf16_tflops_sustained"],
+            "model_tflops": vps * gf / 1e3,
+            "frac_of_sustained_bf16_peak": vps * gf / 1e3 / world / peaks["bf16_tflops_sustained"],
             "e2e": {"value": e2e_vps, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches_per_step * args.steps,
@@ -290,7 +304,7 @@ def run_ours(args):
         }
         if infer:
             line["student_infer"] = infer
-        if world == 1 and not args.skip_cpu:
+        if world == 1 and not args.skip_cpu and not finetune:
             v, sec, cores = cpu_baseline(4, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port",
                                     "sample": "2 timed steps of a 4-video batch of the same T+S train step (f32)"}
@@ -307,6 +321,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--workload", default="ts_train", choices=["ts_train", "finetune_cfg4"])
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-infer", action="store_true")
     args = ap.parse_args()

@@ -4,6 +4,7 @@
 #include "evc_host.h"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace evc {
 
@@ -180,14 +181,21 @@ extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
 
 // ------------------------------------------------------------------ BasicLSTM layer, forward over T steps
 // split-K factor for a GEMM with `tiles` output tiles and kb_total 64-deep k blocks: minimise
-// (rounds over the SMs) x (k blocks per split) + a per-round prologue/epilogue cost of ~4 k blocks.
+// (rounds over the SMs) x (k blocks per split + a per-round pipeline fill / epilogue / slab traffic
+// cost worth ~16 k blocks; calibrated on the 5120x1024x4096 recurrent dgrad, where 2 splits win).
 static int pick_split(int tiles, int kb_total) {
+  static int forced = -1;   // experiments: EVC_FORCE_SPLIT=<n> overrides the model for multi-round problems
+  if (forced < 0) {
+    const char* e = getenv("EVC_FORCE_SPLIT");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0 && tiles > num_sms()) return forced;
   int best = 1;
   long long best_cost = -1;
   for (int s = 1; s <= 16; ++s) {
     if (s > 1 && kb_total / s < 4) break;
     const long long rounds = (static_cast<long long>(tiles) * s + num_sms() - 1) / num_sms();
-    const long long cost = rounds * ((kb_total + s - 1) / s + 4);
+    const long long cost = rounds * ((kb_total + s - 1) / s + 16);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
   return best;
