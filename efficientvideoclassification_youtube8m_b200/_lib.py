@@ -15,6 +15,7 @@ SIGNATURES = {
     "evc_version": [],
     "evc_last_error": [],
     "evc_launch_count": [],
+    "evc_debug_set": [I],
     "evc_frames_pack": [P, I, I, I, P, I, I, I, I, P, P, P],
     "evc_frames_pack_u8": [P, P, I, I, I, P, I, I, I, I, P, P, P],
     "evc_num_frames_student": [P, I, I, I, P, P],

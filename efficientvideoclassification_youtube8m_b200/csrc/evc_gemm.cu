@@ -77,13 +77,15 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_debug & 256) ? 1 : 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, c, args);
   count_launch();
   if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(gemm_kernel)");

@@ -275,6 +275,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above touched only this kernel's own shared memory / TMEM: it may overlap the tail of the
+  // previous kernel; global memory is first read below
+  pdl_launch_dependents();
+  pdl_wait();
 
   // work item = CS M-adjacent tiles (one per CTA of the cluster); tiles past tiles_m are all-OOB dummies
   const int tiles_mc = (args.tiles_m + CS - 1) / CS;

@@ -218,6 +218,8 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, lo
                                      const __nv_bfloat16* __restrict__ h_prev, const int* __restrict__ seq_len,
                                      int t, int rows, int H, float* __restrict__ c_out,
                                      __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ gates) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL (see evc_ptx.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int hq = H >> 2;
   if (idx >= static_cast<long long>(rows) * hq) return;
@@ -279,6 +281,8 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, l
                                      const int* __restrict__ seq_len, int t, int rows, int H,
                                      __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dc_out,
                                      float* __restrict__ dh_pass_out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL (see evc_ptx.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int hq = H >> 2;
   if (idx >= static_cast<long long>(rows) * hq) return;
@@ -634,9 +638,18 @@ int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, cons
                          const void* h_prev, const int* seq_len, int t, int rows, int H, float* c_out, void* h_out,
                          void* gates, cudaStream_t stream) {
   const long long n = static_cast<long long>(rows) * (H / 4);
-  lstm_cell_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      z_part, S, part_stride, bias, c_prev, static_cast<const __nv_bfloat16*>(h_prev), seq_len, t, rows, H, c_out,
-      static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(gates));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, lstm_cell_fwd_kernel, z_part, S, part_stride, bias, c_prev,
+                     static_cast<const __nv_bfloat16*>(h_prev), seq_len, t, rows, H, c_out,
+                     static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(gates));
   count_launch();
   return check_launch("lstm_cell_fwd");
 }
@@ -645,9 +658,18 @@ int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, con
                          const float* dc_in, long long ld_dc_in, const int* seq_len, int t, int rows, int H,
                          void* dz_out, float* dc_out, float* dh_pass_out, cudaStream_t stream) {
   const long long n = static_cast<long long>(rows) * (H / 4);
-  lstm_cell_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      dh_part, S, part_stride, static_cast<const __nv_bfloat16*>(gates), c_prev, dh_ext, ld_dh_ext, dh_pass_in,
-      ld_dh_pass_in, dc_in, ld_dc_in, seq_len, t, rows, H, static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, dh_part, S, part_stride, static_cast<const __nv_bfloat16*>(gates),
+                     c_prev, dh_ext, ld_dh_ext, dh_pass_in, ld_dh_pass_in, dc_in, ld_dc_in, seq_len, t, rows, H,
+                     static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out);
   count_launch();
   return check_launch("lstm_cell_bwd");
 }

@@ -35,6 +35,9 @@ const char* evc_last_error(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 long long evc_launch_count(void);
 
+/* profiling experiments only: bit flags that disable parts of the GEMM epilogues (scripts/exp_*.py) */
+int evc_debug_set(int flags);
+
 /* ---- input: tf.nn.l2_normalize (train.py:256) + uniform gather (train.py:265-272) or
  * gather_nd of sampled frames (model_utils.py:34-36,55-58), fused with the split into
  * num_chunks sub-sequences (frame_level_models.py:237,307).
