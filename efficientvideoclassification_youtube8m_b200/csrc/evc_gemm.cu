@@ -5,6 +5,9 @@
 
 #include <cudaTypedefs.h>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 namespace evc {
 
@@ -24,9 +27,41 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [outer][inner] with row pitch `pitch_elems`; box = box_inner x box_outer, 128B swizzle.
+// Tensor maps are pure functions of (pointer, extents, pitch, box, element size).  The step replays
+// the same few hundred operand descriptors every iteration, so they are cached: encoding them anew
+// cost ~40 % of the host-side launch time of a training step.
+struct TmapKey {
+  const void* ptr;
+  uint64_t inner, outer, pitch;
+  uint32_t box_inner, box_outer, elem;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch == o.pitch && box_inner == o.box_inner &&
+           box_outer == o.box_outer && elem == o.elem;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner * 0xC2B2AE3D27D4EB4Full) ^ (k.outer << 21) ^ (k.pitch << 7) ^ (static_cast<uint64_t>(k.box_inner) << 50) ^
+         (static_cast<uint64_t>(k.box_outer) << 40) ^ k.elem;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+
+// 2-D tensor [outer][inner] (bf16 or f32) with row pitch `pitch_elems`; box = box_inner x box_outer, 128B swizzle.
 static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                      uint32_t box_inner, uint32_t box_outer, int elem_bytes = 2) {
+  const TmapKey key{ptr, inner, outer, pitch_elems, box_inner, box_outer, static_cast<uint32_t>(elem_bytes)};
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *m = it->second;
+      return EVC_OK;
+    }
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * elem_bytes) % 16 != 0)
@@ -36,10 +71,14 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                  const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();   // callers that churn buffers: bound the memory
+    g_tmap_cache.emplace(key, *m);
+  }
   return EVC_OK;
 }
 
