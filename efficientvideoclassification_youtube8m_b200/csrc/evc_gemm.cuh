@@ -441,7 +441,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (args.debug & 16) tma_store_2d(&tmC, box, col0, ks * args.split_rows + row0);
+              if (args.debug & 512)   // experiment: every tile stores into the same 128x256 region (stays in L2)
+                tma_store_2d(&tmC, box, c0, q * 32);
+              else if (args.debug & 16) tma_store_2d(&tmC, box, col0, ks * args.split_rows + row0);
               else if (!(args.debug & 32))   // streamed output must not evict the L2-resident operands
                 tma_store_2d_hint(&tmC, box, col0, ks * args.split_rows + row0, kL2EvictFirst);
               tma_store_commit();

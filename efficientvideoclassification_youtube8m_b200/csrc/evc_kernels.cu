@@ -13,6 +13,29 @@ using namespace evc;
 
 namespace {
 
+// All kernels of this file are launched with programmatic stream serialization: each starts with
+// griddepcontrol.launch_dependents / griddepcontrol.wait (PDL_PROLOGUE) so that its launch latency
+// overlaps the tail of the previous kernel while it still observes all of that kernel's writes.
+#define PDL_PROLOGUE()                                                   \
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");        \
+  asm volatile("griddepcontrol.wait;" ::: "memory")
+
+template <typename... KArgs, typename... Args>
+static cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -42,6 +65,7 @@ __global__ void frames_pack_kernel(const float* __restrict__ src, int B, int T, 
                                    const int* __restrict__ frame_idx, int idx_per_batch, int K, int C,
                                    int normalize, __nv_bfloat16* __restrict__ out_bf16,
                                    float* __restrict__ out_f32) {
+  PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * K) return;
@@ -85,6 +109,7 @@ __global__ void frames_pack_u8_kernel(const uint8_t* __restrict__ src, const int
                                       int T, int D, const int* __restrict__ frame_idx, int idx_per_batch, int K,
                                       int C, int normalize, __nv_bfloat16* __restrict__ out_bf16,
                                       float* __restrict__ out_f32) {
+  PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * K) return;
@@ -133,6 +158,7 @@ __global__ void frames_pack_u8_kernel(const uint8_t* __restrict__ src, const int
 // train.py:263-264  int64( (n / 300) * int(300/every_n) ) in float64
 __global__ void num_frames_student_kernel(const int* __restrict__ nf, int B, int max_frames, int m,
                                           long long* __restrict__ out) {
+  PDL_PROLOGUE();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double q = static_cast<double>(nf[b]) / static_cast<double>(max_frames);
@@ -143,6 +169,7 @@ __global__ void num_frames_student_kernel(const int* __restrict__ nf, int B, int
 //   len_l1[c*B+b] = min(ell, max(0, n - ell*c));  len_l2[b] = int32(ceil(float32(n)/ell))
 __global__ void lstm_lengths_kernel(const void* __restrict__ nf, int is64, int B, int C, int ell,
                                     int* __restrict__ len_l1, int* __restrict__ len_l2) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i / B, b = i % B;
@@ -157,6 +184,7 @@ __global__ void lstm_lengths_kernel(const void* __restrict__ nf, int is64, int B
 // model_utils.py:49-53  int32(u * float32(n))
 __global__ void random_frame_index_kernel(const float* __restrict__ u, const int* __restrict__ nf, int B, int K,
                                           int* __restrict__ idx) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   idx[i] = static_cast<int>(__fmul_rn(u[i], static_cast<float>(nf[i / K])));
@@ -164,6 +192,7 @@ __global__ void random_frame_index_kernel(const float* __restrict__ u, const int
 // model_utils.py:23-33  start = int32(u*float32(max(n-K,0)+1)); idx = min(start+k, n-1)
 __global__ void random_sequence_index_kernel(const float* __restrict__ u, const int* __restrict__ nf, int B, int K,
                                              int* __restrict__ idx) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   const int b = i / K, k = i % K;
@@ -178,6 +207,7 @@ __global__ void random_sequence_index_kernel(const float* __restrict__ u, const 
 __global__ void state_pack_kernel(const float* __restrict__ c0, const __nv_bfloat16* __restrict__ h0,
                                   const float* __restrict__ c1, const __nv_bfloat16* __restrict__ h1, long long n,
                                   int H, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  PDL_PROLOGUE();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long r = i / H;
@@ -348,6 +378,7 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, l
 // f32 [R,C] -> bf16 [R,ld] (columns C..ld-1 zero): bf16 operand copies of weights / activations
 __global__ void cast_bf16_kernel(const float* __restrict__ src, long long R, int C, int ld,
                                  __nv_bfloat16* __restrict__ dst) {
+  PDL_PROLOGUE();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= R * ld) return;
   const long long r = i / ld;
@@ -373,6 +404,7 @@ __device__ __forceinline__ float moe_class(const float* g, const float* e, int M
 
 __global__ void moe_mix_fwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
                                    long long lde, int V, int M, float* __restrict__ p_out) {
+  PDL_PROLOGUE();
   const int b = blockIdx.x;
   const float* g = G + b * ldg;
   const float* e = E + b * lde;
@@ -388,6 +420,7 @@ __global__ void moe_mix_bwd_kernel(const float* __restrict__ G, long long ldg, c
                                    long long lde, const float* __restrict__ dP, int V, int M,
                                    __nv_bfloat16* __restrict__ dG, long long lddg, __nv_bfloat16* __restrict__ dE,
                                    long long ldde) {
+  PDL_PROLOGUE();
   const int b = blockIdx.x;
   const float* g = G + b * ldg;
   const float* e = E + b * lde;
@@ -411,6 +444,7 @@ __global__ void ce_kl_loss_kernel(const float* __restrict__ P, const float* __re
                                   const uint8_t* __restrict__ labels, int V, float ce_scale, float kl_scale,
                                   float* __restrict__ ce_rows, float* __restrict__ kl_rows,
                                   float* __restrict__ dP) {
+  PDL_PROLOGUE();
   __shared__ float sh[32];
   const int b = blockIdx.x;
   const float* p = P + static_cast<long long>(b) * V;
@@ -453,6 +487,7 @@ __global__ void ce_kl_loss_kernel(const float* __restrict__ P, const float* __re
 
 // out[0] = scale * sum_i rows[i]  (reduce_mean / reduce_sum over the batch); single block
 __global__ void reduce_rows_kernel(const float* __restrict__ rows, int n, float scale, float* __restrict__ out) {
+  PDL_PROLOGUE();
   __shared__ float sh[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += rows[i];
@@ -463,6 +498,7 @@ __global__ void reduce_rows_kernel(const float* __restrict__ rows, int n, float 
 // [TF adam.py _prepare/_finish] t += 1 ; lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
 __global__ void adam_lr_kernel(long long* __restrict__ step, float lr, float b1, float b2,
                                float* __restrict__ lr_t) {
+  PDL_PROLOGUE();
   const long long t = step[0] + 1;
   step[0] = t;
   const double td = static_cast<double>(t);
@@ -473,6 +509,7 @@ __global__ void adam_lr_kernel(long long* __restrict__ step, float lr, float b1,
 // train.py:359-362  L_REP rows = sum_j (t - s)^2 ;  dS = grad_scale * (s - t)
 __global__ void rep_loss_kernel(const float* __restrict__ t_state, const float* __restrict__ s_state, int S,
                                 float grad_scale, float* __restrict__ rows, float* __restrict__ d_s) {
+  PDL_PROLOGUE();
   __shared__ float sh[32];
   const int b = blockIdx.x;
   float acc = 0.f;
@@ -489,6 +526,7 @@ __global__ void rep_loss_kernel(const float* __restrict__ t_state, const float* 
 // bias gradients: out[n] += sum_r X[r, n]  (bf16 X with row pitch ld).  out must be zeroed.
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long R, int N, long long ld,
                                    long long rows_per_block, float* __restrict__ out) {
+  PDL_PROLOGUE();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const long long r0 = blockIdx.y * rows_per_block;
@@ -502,6 +540,7 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long lon
 // gradient of penalty * l2_regularizer(1e-8)(w), video_level_models.py:428,434 / train.py:324)
 __global__ void sumsq_kernel(const float* __restrict__ g, const float* __restrict__ w, float wd, long long n,
                              float* __restrict__ out, float* __restrict__ out_wsq) {
+  PDL_PROLOGUE();
   __shared__ float sh[32];
   float acc = 0.f, wacc = 0.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
@@ -537,6 +576,7 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
                                  float* __restrict__ v, long long n, const float* __restrict__ normsq, float clip,
                                  float wd, const float* __restrict__ lr_t, float b1, float b2, float eps,
                                  __nv_bfloat16* __restrict__ shadow, int cols, long long ld_shadow) {
+  PDL_PROLOGUE();
   float scale = 1.f;
   if (clip > 0.f) {
     const float ns = *normsq;
@@ -578,6 +618,7 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
 // lower class index wins and the output is ordered by value descending.  One block per video.
 __global__ void topk_kernel(const float* __restrict__ P, int V, int k, const uint8_t* __restrict__ labels,
                             int* __restrict__ idx_out, float* __restrict__ val_out, uint8_t* __restrict__ lab_out) {
+  PDL_PROLOGUE();
   extern __shared__ unsigned long long keys[];  // V keys + 32 scratch
   unsigned long long* red = keys + V;
   const int b = blockIdx.x;
@@ -618,6 +659,7 @@ __global__ void topk_kernel(const float* __restrict__ P, int V, int k, const uin
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
+  PDL_PROLOGUE();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
@@ -684,7 +726,7 @@ extern "C" int evc_frames_pack(const float* src, int B, int T, int D, const int*
   const long long warps = static_cast<long long>(B) * K;
   const int block = 256;
   const int grid = static_cast<int>((warps * 32 + block - 1) / block);
-  frames_pack_kernel<<<grid, block, 0, EVC_STREAM(stream)>>>(src, B, T, D, frame_idx, idx_per_batch, K, num_chunks,
+  pdl_launch(frames_pack_kernel, dim3(grid), dim3(block), 0, EVC_STREAM(stream), src, B, T, D, frame_idx, idx_per_batch, K, num_chunks,
                                                              normalize, static_cast<__nv_bfloat16*>(out_bf16),
                                                              out_f32);
   count_launch();
@@ -702,7 +744,7 @@ extern "C" int evc_frames_pack_u8(const unsigned char* src, const int* num_frame
   const long long warps = static_cast<long long>(B) * K;
   const int block = 256;
   const int grid = static_cast<int>((warps * 32 + block - 1) / block);
-  frames_pack_u8_kernel<<<grid, block, 0, EVC_STREAM(stream)>>>(src, num_frames, B, T, D, frame_idx, idx_per_batch, K,
+  pdl_launch(frames_pack_u8_kernel, dim3(grid), dim3(block), 0, EVC_STREAM(stream), src, num_frames, B, T, D, frame_idx, idx_per_batch, K,
                                                                 num_chunks, normalize,
                                                                 static_cast<__nv_bfloat16*>(out_bf16), out_f32);
   count_launch();
@@ -712,7 +754,7 @@ extern "C" int evc_frames_pack_u8(const unsigned char* src, const int* num_frame
 extern "C" int evc_num_frames_student(const int* num_frames, int B, int max_frames, int every_n, long long* out,
                                       void* stream) {
   if (every_n <= 0) return set_error(EVC_ERR_ARG, "num_frames_student: every_n must be positive");
-  num_frames_student_kernel<<<(B + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(num_frames, B, max_frames,
+  pdl_launch(num_frames_student_kernel, dim3((B + 127) / 128), dim3(128), 0, EVC_STREAM(stream), num_frames, B, max_frames,
                                                                              max_frames / every_n, out);
   count_launch();
   return check_launch("num_frames_student");
@@ -721,20 +763,20 @@ extern "C" int evc_num_frames_student(const int* num_frames, int B, int max_fram
 extern "C" int evc_lstm_lengths(const void* num_frames, int is_int64, int B, int num_chunks, int chunk_len,
                                 int* len_l1, int* len_l2, void* stream) {
   const int n = B * num_chunks;
-  lstm_lengths_kernel<<<(n + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(num_frames, is_int64, B, num_chunks,
+  pdl_launch(lstm_lengths_kernel, dim3((n + 127) / 128), dim3(128), 0, EVC_STREAM(stream), num_frames, is_int64, B, num_chunks,
                                                                        chunk_len, len_l1, len_l2);
   count_launch();
   return check_launch("lstm_lengths");
 }
 
 extern "C" int evc_random_frame_index(const float* u, const int* num_frames, int B, int K, int* idx, void* stream) {
-  random_frame_index_kernel<<<(B * K + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(u, num_frames, B, K, idx);
+  pdl_launch(random_frame_index_kernel, dim3((B * K + 127) / 128), dim3(128), 0, EVC_STREAM(stream), u, num_frames, B, K, idx);
   count_launch();
   return check_launch("random_frame_index");
 }
 extern "C" int evc_random_sequence_index(const float* u, const int* num_frames, int B, int K, int* idx,
                                          void* stream) {
-  random_sequence_index_kernel<<<(B * K + 127) / 128, 128, 0, EVC_STREAM(stream)>>>(u, num_frames, B, K, idx);
+  pdl_launch(random_sequence_index_kernel, dim3((B * K + 127) / 128), dim3(128), 0, EVC_STREAM(stream), u, num_frames, B, K, idx);
   count_launch();
   return check_launch("random_sequence_index");
 }
@@ -742,7 +784,7 @@ extern "C" int evc_random_sequence_index(const float* u, const int* num_frames, 
 extern "C" int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,
                               void* out_bf16, float* out_f32, void* stream) {
   const long long n = static_cast<long long>(rows) * H;
-  state_pack_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, EVC_STREAM(stream)>>>(
+  pdl_launch(state_pack_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, EVC_STREAM(stream), 
       c0, static_cast<const __nv_bfloat16*>(h0), c1, static_cast<const __nv_bfloat16*>(h1), n, H,
       static_cast<__nv_bfloat16*>(out_bf16), out_f32);
   count_launch();
@@ -752,7 +794,7 @@ extern "C" int evc_state_pack(const float* c0, const void* h0, const float* c1, 
 extern "C" int evc_cast_bf16(const float* src, long long rows, int cols, int ld, void* dst, void* stream) {
   if (ld < cols) return set_error(EVC_ERR_ARG, "cast_bf16: ld < cols");
   const long long n = rows * ld;
-  cast_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, EVC_STREAM(stream)>>>(
+  pdl_launch(cast_bf16_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, EVC_STREAM(stream), 
       src, rows, cols, ld, static_cast<__nv_bfloat16*>(dst));
   count_launch();
   return check_launch("cast_bf16");
@@ -762,7 +804,7 @@ extern "C" int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, lo
                                float* p_out, void* stream) {
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix: 1 <= num_mixtures <= 8");
   if (B <= 0) return EVC_OK;
-  moe_mix_fwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, V, M, p_out);
+  pdl_launch(moe_mix_fwd_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, V, M, p_out);
   count_launch();
   return check_launch("moe_mix_fwd");
 }
@@ -771,7 +813,7 @@ extern "C" int evc_moe_mix_bwd(const float* G, long long ldg, const float* E, lo
                                int V, int M, void* dG, long long lddg, void* dE, long long ldde, void* stream) {
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix_bwd: 1 <= num_mixtures <= 8");
   if (B <= 0) return EVC_OK;
-  moe_mix_bwd_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(G, ldg, E, lde, dP, V, M, static_cast<__nv_bfloat16*>(dG),
+  pdl_launch(moe_mix_bwd_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, dP, V, M, static_cast<__nv_bfloat16*>(dG),
                                                         lddg, static_cast<__nv_bfloat16*>(dE), ldde);
   count_launch();
   return check_launch("moe_mix_bwd");
@@ -782,26 +824,26 @@ extern "C" int evc_ce_kl_loss(const float* P, const float* PT, const unsigned ch
                               void* stream) {
   if (labels == nullptr && PT == nullptr) return set_error(EVC_ERR_ARG, "ce_kl_loss: labels or teacher needed");
   if (B <= 0) return EVC_OK;
-  ce_kl_loss_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(P, PT, labels, V, ce_scale, kl_scale, ce_rows, kl_rows, dP);
+  pdl_launch(ce_kl_loss_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), P, PT, labels, V, ce_scale, kl_scale, ce_rows, kl_rows, dP);
   count_launch();
   return check_launch("ce_kl_loss");
 }
 
 extern "C" int evc_reduce_rows(const float* rows, int n, float scale, float* out, void* stream) {
-  reduce_rows_kernel<<<1, 256, 0, EVC_STREAM(stream)>>>(rows, n, scale, out);
+  pdl_launch(reduce_rows_kernel, dim3(1), dim3(256), 0, EVC_STREAM(stream), rows, n, scale, out);
   count_launch();
   return check_launch("reduce_rows");
 }
 
 extern "C" int evc_adam_lr(long long* step, float lr, float beta1, float beta2, float* lr_t, void* stream) {
-  adam_lr_kernel<<<1, 1, 0, EVC_STREAM(stream)>>>(step, lr, beta1, beta2, lr_t);
+  pdl_launch(adam_lr_kernel, dim3(1), dim3(1), 0, EVC_STREAM(stream), step, lr, beta1, beta2, lr_t);
   count_launch();
   return check_launch("adam_lr");
 }
 
 extern "C" int evc_rep_loss(const float* teacher_state, const float* student_state, int B, int S, float grad_scale,
                             float* rows, float* d_student, void* stream) {
-  rep_loss_kernel<<<B, 256, 0, EVC_STREAM(stream)>>>(teacher_state, student_state, S, grad_scale, rows, d_student);
+  pdl_launch(rep_loss_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), teacher_state, student_state, S, grad_scale, rows, d_student);
   count_launch();
   return check_launch("rep_loss");
 }
@@ -811,14 +853,14 @@ extern "C" int evc_colsum_bf16(const void* X, long long rows, int N, long long l
   long long gy = (rows + rpb - 1) / rpb;
   if (gy > 2048) { gy = 2048; rpb = (rows + gy - 1) / gy; gy = (rows + rpb - 1) / rpb; }
   dim3 grid((N + 127) / 128, static_cast<unsigned>(gy));
-  colsum_bf16_kernel<<<grid, 128, 0, EVC_STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(X), rows, N, ld, rpb,
+  pdl_launch(colsum_bf16_kernel, dim3(grid), dim3(128), 0, EVC_STREAM(stream), static_cast<const __nv_bfloat16*>(X), rows, N, ld, rpb,
                                                            out);
   count_launch();
   return check_launch("colsum_bf16");
 }
 
 extern "C" int evc_fill_f32(float* p, long long n, float value, void* stream) {
-  fill_f32_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(p, n, value);
+  pdl_launch(fill_f32_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, EVC_STREAM(stream), p, n, value);
   count_launch();
   return check_launch("fill_f32");
 }
@@ -827,7 +869,7 @@ extern "C" int evc_sumsq(const float* g, const float* w, float weight_decay, lon
                          float* out_wsq, void* stream) {
   if ((reinterpret_cast<uintptr_t>(g) & 15) || (w && (reinterpret_cast<uintptr_t>(w) & 15)))
     return set_error(EVC_ERR_ARG, "sumsq: pointers must be 16-byte aligned");
-  sumsq_kernel<<<grid_for((n + 3) / 4, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(g, w, w ? weight_decay : 0.f, n,
+  pdl_launch(sumsq_kernel, dim3(grid_for((n + 3) / 4, 256, 148 * 8)), dim3(256), 0, EVC_STREAM(stream), g, w, w ? weight_decay : 0.f, n,
                                                                                     out, w ? out_wsq : nullptr);
   count_launch();
   return check_launch("sumsq");
@@ -841,7 +883,7 @@ extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long 
       ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
         reinterpret_cast<uintptr_t>(v)) & 15))
     return set_error(EVC_ERR_ARG, "clip_adam: tensors must be 16-byte aligned with sizes/cols multiple of 4");
-  clip_adam_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, EVC_STREAM(stream)>>>(
+  pdl_launch(clip_adam_kernel, dim3(grid_for(n / 4, 256, 148 * 8)), dim3(256), 0, EVC_STREAM(stream), 
       w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps,
       static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow);
   count_launch();
@@ -859,7 +901,7 @@ extern "C" int evc_topk(const float* P, int B, int V, int k, const unsigned char
     cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  topk_kernel<<<B, 256, smem, EVC_STREAM(stream)>>>(P, V, k, labels, idx_out, val_out, lab_out);
+  pdl_launch(topk_kernel, dim3(B), dim3(256), smem, EVC_STREAM(stream), P, V, k, labels, idx_out, val_out, lab_out);
   count_launch();
   return check_launch("topk");
 }
