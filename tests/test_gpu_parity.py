@@ -223,3 +223,36 @@ def test_loss_curve_200_steps():
     rel = _curve(1e-3, 100)
     assert rel["l_ce"].max() < 0.015, rel["l_ce"].max()
     assert np.median(rel["student_loss"]) < 0.01 and np.median(rel["teacher_loss"]) < 0.01
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_ragged_tiny_batches_and_empty_video(B):
+    """Edge cases: batch smaller than any tile (rows 20*B / 5*B < 128), a video with num_frames = 0 (all
+    lengths zero -> zero state -> p = sum_m softmax(0)[m]*sigmoid(b)), one with a single frame."""
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import TeacherStudentTrainer
+    cfg = ModelConfig(**SMALL)
+    x, nf, lab = O.synthetic_batch(B, seed=77, num_features=cfg.feature_size, vocab_size=cfg.vocab_size)
+    nf[0] = 0
+    x[0] = 0.0
+    tr = TeacherStudentTrainer(cfg, batch_size=B, lstm_gain=2.0)
+    T = O.init_params("model", 0, dtype=torch.float64, gain=2.0, **SMALL)
+    S = O.init_params("model_student", 1, dtype=torch.float64, gain=2.0, **SMALL)
+    tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda(),
+                        torch.from_numpy(lab).cuda().view(torch.uint8))
+    torch.cuda.synchronize()
+    ref = O.teacher_student_train_step(torch.from_numpy(x).double(), nf, torch.from_numpy(lab), T, S, None, None,
+                                       clip_gradient_norm=0.0, regularization_penalty=0.0,
+                                       vocab_size=cfg.vocab_size, num_mixtures=cfg.num_mixtures)
+    assert torch.all(tr.t_eng.state[0] == 0) and torch.all(tr.s_eng.state[0] == 0)
+    assert (tr.t_eng.pred.cpu().double() - ref["teacher_predictions"]).abs().max().item() < 1e-3
+    assert (tr.s_eng.pred.cpu().double() - ref["student_predictions"]).abs().max().item() < 1e-3
+    for params, grads in [(tr.teacher, ref["teacher_grads"]), (tr.student, ref["student_grads"])]:
+        for n in params.names:
+            g, r = params.g[n].cpu().double(), grads[n]
+            den = r.norm().item()
+            if den < 1e-12:
+                assert g.norm().item() < 1e-6, n
+            else:
+                assert ((g - r).norm() / den).item() < 3e-2, n
