@@ -177,6 +177,76 @@ class HLstmParams:
             rows, cols = self.shapes[n]
             ops.cast_bf16(self.w[n], s, rows, cols, self.ld[n])
 
+    # ---- data-parallel optimizer sharding (ZeRO-1 style): every matrix is split into `world` row blocks; a
+    # rank receives the averaged gradient of its block (reduce-scatter), updates only those rows of the f32
+    # master / Adam moments, and the refreshed bf16 operand rows are all-gathered.  Biases stay replicated.
+    def matrix_names(self) -> List[str]:
+        return [n for n in self.names if len(self.shapes[n]) == 2]
+
+    def vector_names(self) -> List[str]:
+        return [n for n in self.names if len(self.shapes[n]) == 1]
+
+    def row_block(self, n: str, rank: int, world: int):
+        rows = self.shapes[n][0]
+        if rows % world != 0:
+            raise ValueError(f"{n}: {rows} rows do not split over {world} ranks")
+        per = rows // world
+        return rank * per, (rank + 1) * per
+
+    def apply_gradients_sharded(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
+                                rank: int, world: int, group=None, beta1: float = 0.9, beta2: float = 0.999,
+                                eps: float = 1e-8):
+        """Same update as apply_gradients for the rows this rank owns.  Expects the matrix gradients
+        reduce-scattered (owned rows = average over ranks) and the bias gradients all-reduced.  Returns the
+        async all-gather handles of the bf16 operand copies (wait before the next forward)."""
+        import torch.distributed as dist
+        wd = float(regularization_penalty) * self.cfg.l2_penalty
+        ops.fill_f32(self.normsq, 0.0)
+        ops.fill_f32(self.wsq, 0.0)
+        ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
+        reg = (self.gates_w, self.experts_w)
+        idx = {n: i for i, n in enumerate(self.names)}
+        blocks = {}
+        for n in self.matrix_names():
+            r0, r1 = self.row_block(n, rank, world)
+            blocks[n] = (r0, r1)
+            i = idx[n]
+            w = self.w[n][r0:r1] if n in reg else None
+            ops.sumsq(self.g[n][r0:r1], w, wd, self.normsq[i:i + 1], self.wsq[i:i + 1] if w is not None else None)
+        # per-variable norms need the other ranks' row blocks: two tiny SUM all-reduces (11 floats each)
+        dist.all_reduce(self.normsq, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.wsq, op=dist.ReduceOp.SUM, group=group)
+        for n in self.vector_names():
+            i = idx[n]
+            ops.sumsq(self.g[n], None, 0.0, self.normsq[i:i + 1], None)
+        handles = []
+        for n in self.names:
+            i = idx[n]
+            if n in blocks:
+                r0, r1 = blocks[n]
+                cols, ld = self.shapes[n][1], self.ld[n]
+                ops.clip_adam(self.w[n][r0:r1], self.g[n][r0:r1], self.m[n][r0:r1], self.v[n][r0:r1],
+                              self.normsq[i:i + 1], float(clip_gradient_norm), wd if n in reg else 0.0, self.lr_t,
+                              beta1, beta2, eps, self.shadow[n][r0:r1], cols, ld)
+                handles.append(dist.all_gather_into_tensor(self.shadow[n], self.shadow[n][r0:r1], group=group,
+                                                           async_op=True))
+            else:
+                ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],
+                              float(clip_gradient_norm), 0.0, self.lr_t, beta1, beta2, eps, None, 0, 0)
+        self._master_stale = world > 1
+        return handles
+
+    def sync_master_weights(self, rank: int, world: int, group=None) -> None:
+        """After sharded updates only the owned rows of the f32 masters are current: gather the rest
+        (needed before state_dict()/save(), not on the training path)."""
+        import torch.distributed as dist
+        if world <= 1 or not getattr(self, "_master_stale", False):
+            return
+        for n in self.matrix_names():
+            r0, r1 = self.row_block(n, rank, world)
+            dist.all_gather_into_tensor(self.w[n], self.w[n][r0:r1].clone(), group=group)
+        self._master_stale = False
+
     # ---- slim.learning.create_train_op: per-variable clip_by_norm + Adam (train.py:329-334)
     def apply_gradients(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
                         beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:

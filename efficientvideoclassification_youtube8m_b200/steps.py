@@ -45,7 +45,8 @@ def _as_u8(labels: torch.Tensor) -> torch.Tensor:
 
 class _Base:
     def __init__(self, cfg: ModelConfig, batch_size: int, device, every_n: int, num_inputs_L1: int,
-                 base_learning_rate: float, clip_gradient_norm: float, regularization_penalty: float):
+                 base_learning_rate: float, clip_gradient_norm: float, regularization_penalty: float,
+                 shard_optimizer: Optional[bool] = None):
         self.cfg, self.B, self.device = cfg, batch_size, torch.device(device)
         self.every_n, self.num_inputs_L1 = every_n, num_inputs_L1
         self.lr, self.clip, self.penalty = base_learning_rate, clip_gradient_norm, regularization_penalty
@@ -58,6 +59,9 @@ class _Base:
         self.nf_student = torch.zeros(batch_size, dtype=torch.int64, device=self.device)
         self.global_step = 0
         self._pending = []
+        self._gathers = []
+        # optimizer sharding over the data-parallel ranks (on by default when there is more than one)
+        self.shard_optimizer = shard_optimizer if shard_optimizer is not None else (self._world() > 1)
 
     @staticmethod
     def _world():
@@ -77,6 +81,42 @@ class _Base:
         else:
             dist.all_reduce(buf, op=dist.ReduceOp.SUM)
             buf.div_(n)
+
+    def _reduce_grads(self, params, names):
+        """Average the gradients of `names` over the ranks: whole-buffer all-reduce slices in the replicated
+        mode, per-matrix reduce-scatter (owner keeps the average of its row block) + bias all-reduce in the
+        sharded mode.  Asynchronous on NCCL's stream."""
+        n = self._world()
+        if n <= 1:
+            return
+        if not (self.shard_optimizer and dist.get_backend() == "nccl"):
+            lo = min(params.offsets[x] for x in names)
+            hi = max(params.offsets[x] + params.g[x].numel() for x in names)
+            self._allreduce(params, lo, hi)
+            return
+        rank = dist.get_rank()
+        for x in names:
+            g = params.g[x]
+            if g.dim() == 2:
+                r0, r1 = params.row_block(x, rank, n)
+                w = dist.reduce_scatter_tensor(g[r0:r1], g, op=dist.ReduceOp.AVG, async_op=True)
+            else:
+                w = dist.all_reduce(g, op=dist.ReduceOp.AVG, async_op=True)
+            self._pending.append((params, w))
+
+    def _apply(self, params):
+        """clip + Adam for one parameter set (after its gradient collectives have completed)."""
+        self._finish_allreduce(params)
+        n = self._world()
+        if n > 1 and self.shard_optimizer and dist.get_backend() == "nccl":
+            self._gathers += params.apply_gradients_sharded(self.lr, self.clip, self.penalty, dist.get_rank(), n)
+        else:
+            params.apply_gradients(self.lr, self.clip, self.penalty)
+
+    def _finish_gathers(self):
+        for w in self._gathers:
+            w.wait()
+        self._gathers = []
 
     def _finish_allreduce(self, params=None):
         """Wait for the outstanding collectives (of one parameter set, or all)."""
@@ -110,9 +150,9 @@ class TeacherStudentTrainer(_Base):
                  every_n: int = 10, num_inputs_to_lstm: int = 20, num_inputs_L1: int = 5,
                  base_learning_rate: float = 1e-3, clip_gradient_norm: float = 1.0,
                  regularization_penalty: float = 2.0, teacher_seed: Optional[int] = 0,
-                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0):
+                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
-                         clip_gradient_norm, regularization_penalty)
+                         clip_gradient_norm, regularization_penalty, shard_optimizer)
         self.teacher = HLstmParams("model", cfg, device, teacher_seed, lstm_gain)
         self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
         self.t_eng = HLstmEngine(self.teacher, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=True)
@@ -131,27 +171,27 @@ class TeacherStudentTrainer(_Base):
         s.forward(raw, self.frame_idx, True, self.nf_student, num_frames)
         # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term
         ops.ce_kl_loss(t.pred, None, labels_u8, 1.0 / B, 0.0, self.rows[0], None, t.dP)
-        mo_t, mo_s = self._moe_offset(self.teacher), self._moe_offset(self.student)
         t.classifier_backward(t.dP)
-        self._allreduce(self.teacher, mo_t, None)      # classifier gradients travel during the LSTM backward
+        self._reduce_grads(self.teacher, self.teacher.names[8:])   # classifier gradients travel during the LSTM backward
         t.lstm_backward()
-        self._allreduce(self.teacher, 0, mo_t)
+        self._reduce_grads(self.teacher, self.teacher.names[:8])
         # student loss = 2*L_REP + L_PRED + L_CE + penalty*reg (train.py:359-406); teacher tensors are
         # constants for the student's backward (F9)
         ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
         ops.ce_kl_loss(s.pred, t.pred, labels_u8, 1.0 / B, 1.0, self.rows[1], self.rows[2], s.dP)
         s.classifier_backward(s.dP, dstate_preset=True)
-        self._allreduce(self.student, mo_s, None)
+        self._reduce_grads(self.student, self.student.names[8:])
         s.lstm_backward()
-        self._allreduce(self.student, 0, mo_s)
+        self._reduce_grads(self.student, self.student.names[:8])
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
         ops.reduce_rows(self.rows[1], 1.0 / B, self.losses[1:2])
         ops.reduce_rows(self.rows[2], 1.0, self.losses[2:3])
         ops.reduce_rows(self.rows[3], 1.0 / B, self.losses[3:4])
 
     def apply_gradients(self):
-        self.teacher.apply_gradients(self.lr, self.clip, self.penalty)
-        self.student.apply_gradients(self.lr, self.clip, self.penalty)
+        self._apply(self.teacher)
+        self._apply(self.student)
+        self._finish_gathers()
 
     def step(self, model_input_raw, num_frames, labels) -> None:
         """One iteration = both train ops (global_step += 2).  Asynchronous; read
@@ -159,10 +199,9 @@ class TeacherStudentTrainer(_Base):
         self._check(model_input_raw, num_frames, labels)
         self.forward_backward(model_input_raw, num_frames, _as_u8(labels))
         # the teacher's optimizer pass runs while the student's last gradient slice is still on the wire
-        self._finish_allreduce(self.teacher)
-        self.teacher.apply_gradients(self.lr, self.clip, self.penalty)
-        self._finish_allreduce(self.student)
-        self.student.apply_gradients(self.lr, self.clip, self.penalty)
+        self._apply(self.teacher)
+        self._apply(self.student)
+        self._finish_gathers()
         self.global_step += 2
 
     def fetch(self) -> Dict[str, float]:
@@ -188,9 +227,9 @@ class StudentFinetuneTrainer(_Base):
     def __init__(self, cfg: ModelConfig = ModelConfig(), batch_size: int = 256, device="cuda",
                  every_n: int = 10, num_inputs_L1: int = 5, base_learning_rate: float = 1e-3,
                  clip_gradient_norm: float = 1.0, regularization_penalty: float = 2.0,
-                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0):
+                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
-                         clip_gradient_norm, regularization_penalty)
+                         clip_gradient_norm, regularization_penalty, shard_optimizer)
         self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
         self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
         self.rows = torch.zeros(1, batch_size, dtype=torch.float32, device=self.device)
@@ -203,13 +242,12 @@ class StudentFinetuneTrainer(_Base):
         s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames)
         ops.ce_kl_loss(s.pred, None, _as_u8(labels), 1.0 / B, 0.0, self.rows[0], None, s.dP)
         s.classifier_backward(s.dP)
-        mo = self._moe_offset(self.student)
-        self._allreduce(self.student, mo, None)
+        self._reduce_grads(self.student, self.student.names[8:])
         s.lstm_backward()
-        self._allreduce(self.student, 0, mo)
+        self._reduce_grads(self.student, self.student.names[:8])
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
-        self._finish_allreduce()
-        self.student.apply_gradients(self.lr, self.clip, self.penalty)
+        self._apply(self.student)
+        self._finish_gathers()
         self.global_step += 1
 
     def fetch(self) -> Dict[str, float]:
