@@ -137,8 +137,8 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import hlstm_oracle as O
     from efficientvideoclassification_youtube8m_b200 import _lib, ops
+    from efficientvideoclassification_youtube8m_b200 import synthetic as O   # input generator (no oracle here)
     from efficientvideoclassification_youtube8m_b200.params import ModelConfig
     from efficientvideoclassification_youtube8m_b200.steps import (StudentEvaluator, StudentFinetuneTrainer,
                                                                    TeacherStudentTrainer)

@@ -48,12 +48,12 @@ class EvcError(RuntimeError):
     pass
 
 
-def _load():
-    if not os.path.exists(LIB_PATH):
+def _load(path: str = LIB_PATH):
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            f"{path} not found: the CUDA extension is required (no CPU fallback). "
             "Build it with `python -c 'import __graft_entry__ as g; g.build()'` from the repo root.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -449,6 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               tma_store_commit();
             }
             buf ^= 1;
+            if (args.debug >> 16) __nanosleep(args.debug >> 16);   // experiment: pace the output stores
           }
           if (lane == 0) tma_store_wait_read<0>();              // staging is free again for the next tile
           __syncwarp();

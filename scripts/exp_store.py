@@ -14,8 +14,8 @@ for (M, N, K) in [(76800, 1024, 4096), (5120, 4096, 2176), (5120, 1024, 4096), (
     A = torch.randn(M, K, device="cuda").bfloat16(); B = torch.randn(N, K, device="cuda").bfloat16()
     out = torch.zeros(M, N, device="cuda")
     res = []
-    for flag in [0, 32]:
+    for flag in [0, 250<<16, 500<<16, 1000<<16, 2000<<16, 32]:
         dbg(flag)
-        res.append(f"dbg{flag} {timeit(lambda: ops.gemm(A, B, M, N, K, out)):7.1f}us")
+        res.append(f"dbg{flag>>16 if flag>>16 else flag} {timeit(lambda: ops.gemm(A, B, M, N, K, out)):7.1f}us")
     dbg(0)
     print((M, N, K), " | ".join(res), flush=True)

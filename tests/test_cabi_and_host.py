@@ -100,3 +100,24 @@ def test_average_precision_calculator_matches_reference_golden():
         assert abs(calc.peek_ap_at_n() - float(gold[case + "/gap"])) < 1e-6
     with pytest.raises(ValueError):
         AveragePrecisionCalculator(top_n=-1)
+
+
+def test_missing_extension_fails_loudly(tmp_path):
+    """No CPU fallback: without libevc.so the binding refuses to load, and host tensors are rejected."""
+    import torch
+    from efficientvideoclassification_youtube8m_b200 import _lib, ops
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib._load(str(tmp_path / "libevc.so"))
+    with pytest.raises(ValueError):
+        ops.topk(torch.zeros(2, 30), 5)            # CPU tensor
+
+
+def test_bench_gpu_arm_does_not_import_the_oracle():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    body = src[src.index("def run_ours"):src.index("def main")]
+    assert "oracle" not in body.replace("no oracle here", "")
+    pkg = os.path.join(ROOT, "efficientvideoclassification_youtube8m_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            text = open(os.path.join(pkg, f)).read()
+            assert "import oracle" not in text and "from oracle" not in text, f
