@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM family: tensor-map construction, launch, and the C-ABI entry
 // points evc_gemm_bf16 / evc_lstm_seq_fwd / evc_lstm_seq_bwd declared in include/evc.h.
 #include "evc_gemm.cuh"
+#include "evc_rec.cuh"
 #include "evc_host.h"
 
 #include <cudaTypedefs.h>
@@ -90,6 +91,24 @@ static int make_tmap_a(CUtensorMap* m, const void* p, int a_mn, long long ld, in
 // (cs = cluster size: a K-major B tile is loaded as cs row slices, one per CTA of the cluster)
 static int make_tmap_b(CUtensorMap* m, const void* p, int b_mn, long long ld, int N, int K, int bn, int cs) {
   return b_mn ? make_tmap(m, p, N, K, ld, 64, 64) : make_tmap(m, p, K, N, ld, 64, bn / cs);
+}
+
+// 3-D bf16 tensor [steps][rows][inner] (row pitch = inner, step stride in elements); box 64 x 128 x 1
+static int make_tmap_steps(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t steps,
+                           uint64_t step_stride_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (inner * 2) % 16 != 0 || (step_stride_elems * 2) % 16 != 0)
+    return set_error(EVC_ERR_ARG, "TMA operand must be 16-byte aligned with 16-byte multiple pitches");
+  cuuint64_t dims[3] = {inner, rows, steps};
+  cuuint64_t strides[2] = {inner * 2, step_stride_elems * 2};
+  cuuint32_t box[3] = {64, BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed");
+  return EVC_OK;
 }
 
 constexpr int kCluster = 2;   // CTAs per cluster sharing a multicast B tile
@@ -244,7 +263,15 @@ static int pick_split(int tiles, int kb_total) {
 
 extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
   // forward small-row path: S x rows x 4H f32 ; backward: S x rows x H f32
-  const int sf = (rows <= 1024) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
+  int sf = (rows <= 1024) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
+  {   // the persistent multi-step kernel may use up to 8 slabs
+    const int tiles = ceil_div(rows, BM) * (4 * H / 256);
+    if (tiles <= num_sms()) {
+      int S = num_sms() / tiles;
+      if (S > 8) S = 8;
+      if (S > sf) sf = S;
+    }
+  }
   const int sb = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
   const long long f = static_cast<long long>(sf) * rows * 4 * H * 4;
   const long long b = static_cast<long long>(sb) * rows * H * 4;
@@ -262,6 +289,64 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
   __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
   const long long RH = static_cast<long long>(rows) * H;
   int rc;
+  // EXPERIMENTAL (off unless EVC_PERSISTENT=1): persistent multi-step kernel, every (tile, K split) work item
+  // gets its own resident CTA for all T steps with two grid barriers per step (csrc/evc_rec.cuh).  Measured
+  // on B200 at 256 rows: 32 us/step vs 26 us for split-K GEMM + cell kernel launched with PDL -- the
+  // un-overlapped slab store (8 us) and the two barriers (~3 us each) cost more than the launches they save.
+  {
+    static int persistent = -1;
+    if (persistent < 0) {
+      const char* e = getenv("EVC_PERSISTENT");
+      persistent = e ? atoi(e) : 0;
+    }
+    const int tiles = ceil_div(rows, BM) * (4 * H / 256);
+    if (persistent && workspace != nullptr && T >= 2 && tiles <= num_sms() && H % 64 == 0) {
+      int S = num_sms() / tiles;
+      if (S > 8) S = 8;
+      while (S > 1 && (Kx + H) / BK / S < 8) --S;
+      const long long slab = static_cast<long long>(rows) * 4 * H;
+      if (static_cast<long long>(S) * slab * 4 + 256 > workspace_bytes)
+        return set_error(EVC_ERR_ARG, "lstm_seq_fwd: workspace too small (evc_lstm_workspace_bytes)");
+      unsigned int* bar = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + static_cast<long long>(S) * slab * 4);
+      cudaError_t e = cudaMemsetAsync(bar, 0, 64, stream);
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(barrier)");
+      CUtensorMap tx, th, tw;
+      rc = make_tmap_steps(&tx, xb, Kx, rows, T, x_step_stride);
+      if (rc) return rc;
+      rc = make_tmap_steps(&th, hb, H, rows, T + 1, RH);
+      if (rc) return rc;
+      rc = make_tmap_b(&tw, W, 1, 4LL * H, 4 * H, Kx + H, 256, 1);
+      if (rc) return rc;
+      RecArgs a = {};
+      a.rows = rows; a.H = H; a.T = T;
+      a.tiles_m = ceil_div(rows, BM); a.tiles_n = 4 * H / 256; a.S = S;
+      a.kb_x = Kx / BK; a.kb_h = H / BK;
+      a.bias = bias; a.seq_len = seq_len;
+      a.c_all = c_all; a.h_all = hb; a.gates_all = gb;
+      a.slabs = static_cast<float*>(workspace);
+      a.barrier = bar;
+      static bool configured = false;
+      if (!configured) {
+        e = cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(lstm_rec_fwd)");
+        configured = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(tiles * S);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = GemmCfg<256>::SMEM_BYTES;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, lstm_rec_fwd_kernel, tx, th, tw, a);
+      count_launch();
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(lstm_rec_fwd_kernel)");
+      return check_launch("lstm_rec_fwd_kernel");
+    }
+  }
   if (rows <= 1024 && workspace != nullptr) {
     // Small-row steps (RNN_L2, student): one 128x256 tile per CTA would serialise the whole K on a few
     // SMs.  Split K over the SMs into f32 partial slabs, then one full-occupancy cell kernel sums
