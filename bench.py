@@ -141,7 +141,7 @@ def run_ours(args):
     from efficientvideoclassification_youtube8m_b200 import synthetic as O   # input generator (no oracle here)
     from efficientvideoclassification_youtube8m_b200.params import ModelConfig
     from efficientvideoclassification_youtube8m_b200.steps import (StudentEvaluator, StudentFinetuneTrainer,
-                                                                   TeacherStudentTrainer)
+                                                                   TeacherEvaluator, TeacherStudentTrainer)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -276,7 +276,13 @@ def run_ours(args):
         dxi, dnfi = torch.from_numpy(xi).to(dev), torch.from_numpy(nfi).to(dev)
         ms_inf = timed(lambda: ev.step(dxi, dnfi), 10, 3)
         infer = {"student_infer_videos_per_s": Bi / (ms_inf * 1e-3), "batch": Bi, "ms_per_step": ms_inf}
-        del ev, dxi
+        del ev
+        # the teacher on all 300 frames (validate.py:149-155): denominator of the paper's inference-cost ratio
+        evt = TeacherEvaluator(tr.teacher, Bi)
+        ms_t = timed(lambda: evt.step(dxi, dnfi), 5, 2)
+        infer.update({"teacher_infer_videos_per_s": Bi / (ms_t * 1e-3), "teacher_ms_per_step": ms_t,
+                      "student_speedup_over_teacher": ms_t / ms_inf})
+        del evt, dxi
 
     if rank == 0:
         vps = world * B / (ms_step * 1e-3)
