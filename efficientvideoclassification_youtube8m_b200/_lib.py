@@ -32,6 +32,7 @@ SIGNATURES = {
     "evc_moe_mix_fwd": [P, L, P, L, I, I, I, P, P],
     "evc_moe_mix_bwd": [P, L, P, L, P, I, I, I, P, L, P, L, P],
     "evc_ce_kl_loss": [P, P, P, I, I, F, F, P, P, P, P],
+    "evc_moe_mix_loss": [P, L, P, L, P, P, I, I, I, F, F, P, P, P, P, L, P, L, P],
     "evc_reduce_rows": [P, I, F, P, P],
     "evc_adam_lr": [P, F, F, F, P, P],
     "evc_rep_loss": [P, P, I, I, F, P, P, P],

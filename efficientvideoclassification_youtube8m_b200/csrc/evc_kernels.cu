@@ -485,6 +485,66 @@ __global__ void ce_kl_loss_kernel(const float* __restrict__ P, const float* __re
   }
 }
 
+// Fused classifier head of the training step (video_level_models.py:437-447 + losses.py:90-97 +
+// train.py:398-402): mixture forward, CE row, KL(teacher || student) row, d(loss)/dp and the
+// gradients w.r.t. the gate / expert logits in ONE launch per model (one block per video).
+//   pass 1: p[c] (written, kept in L2) and, for the KL normalisers, sum p and sum pT
+//   pass 2: CE/KL terms, dp = ce_scale*dCE/dp + kl_scale*dKL/dp, dG/dE (bf16 GEMM operands)
+__global__ void moe_mix_loss_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
+                                    long long lde, const float* __restrict__ PT,
+                                    const uint8_t* __restrict__ labels, int V, int M, float ce_scale,
+                                    float kl_scale, float* __restrict__ P, float* __restrict__ ce_rows,
+                                    float* __restrict__ kl_rows, __nv_bfloat16* __restrict__ dG, long long lddg,
+                                    __nv_bfloat16* __restrict__ dE, long long ldde) {
+  PDL_PROLOGUE();
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* g = G + b * ldg;
+  const float* e = E + b * lde;
+  float* p = P + static_cast<long long>(b) * V;
+  const float* pt = PT ? PT + static_cast<long long>(b) * V : nullptr;
+  const uint8_t* y8 = labels + static_cast<long long>(b) * V;
+  float ss = 0.f, st = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float gate[9], sig[8];
+    const float pc = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
+    p[c] = pc;
+    ss += pc;
+    if (pt) st += pt[c];
+  }
+  float inv_sT = 0.f, inv_sS = 0.f;
+  if (pt) {
+    ss = block_sum(ss, sh);
+    st = block_sum(st, sh);
+    inv_sS = 1.0f / ss;
+    inv_sT = 1.0f / st;
+  }
+  float ce = 0.f, kl = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float gate[9], sig[8];
+    const float pc = moe_class<8>(g + c * (M + 1), e + c * M, M, gate, sig);
+    const float y = y8[c] ? 1.f : 0.f;
+    ce -= y * __logf(pc + 1e-5f) + (1.f - y) * __logf(1.f - pc + 1e-5f);
+    float dp = ce_scale * (-(y / (pc + 1e-5f)) + (1.f - y) / (1.f - pc + 1e-5f));
+    if (pt) {
+      const float th = pt[c] * inv_sT;
+      dp += kl_scale * (-th / pc + inv_sS);
+      if (th > 0.f) kl += th * (__logf(th) - __logf(pc * inv_sS));
+    }
+    for (int m = 0; m <= M; ++m) {
+      const float sgm = (m < M) ? sig[m] : 0.f;
+      dG[b * lddg + c * (M + 1) + m] = __float2bfloat16(gate[m] * (sgm - pc) * dp);
+    }
+    for (int m = 0; m < M; ++m) dE[b * ldde + c * M + m] = __float2bfloat16(gate[m] * sig[m] * (1.f - sig[m]) * dp);
+  }
+  ce = block_sum(ce, sh);
+  if (threadIdx.x == 0) ce_rows[b] = ce;
+  if (kl_rows) {
+    kl = block_sum(kl, sh);
+    if (threadIdx.x == 0) kl_rows[b] = kl;
+  }
+}
+
 // out[0] = scale * sum_i rows[i]  (reduce_mean / reduce_sum over the batch); single block
 __global__ void reduce_rows_kernel(const float* __restrict__ rows, int n, float scale, float* __restrict__ out) {
   PDL_PROLOGUE();
@@ -827,6 +887,19 @@ extern "C" int evc_ce_kl_loss(const float* P, const float* PT, const unsigned ch
   pdl_launch(ce_kl_loss_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), P, PT, labels, V, ce_scale, kl_scale, ce_rows, kl_rows, dP);
   count_launch();
   return check_launch("ce_kl_loss");
+}
+
+extern "C" int evc_moe_mix_loss(const float* G, long long ldg, const float* E, long long lde, const float* PT,
+                                const unsigned char* labels, int B, int V, int M, float ce_scale, float kl_scale,
+                                float* P, float* ce_rows, float* kl_rows, void* dG, long long lddg, void* dE,
+                                long long ldde, void* stream) {
+  if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix_loss: 1 <= num_mixtures <= 8");
+  if (labels == nullptr || ce_rows == nullptr) return set_error(EVC_ERR_ARG, "moe_mix_loss: labels and ce_rows required");
+  if (B <= 0) return EVC_OK;
+  pdl_launch(moe_mix_loss_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, PT, labels, V, M, ce_scale,
+             kl_scale, P, ce_rows, kl_rows, static_cast<__nv_bfloat16*>(dG), lddg, static_cast<__nv_bfloat16*>(dE), ldde);
+  count_launch();
+  return check_launch("moe_mix_loss");
 }
 
 extern "C" int evc_reduce_rows(const float* rows, int n, float scale, float* out, void* stream) {

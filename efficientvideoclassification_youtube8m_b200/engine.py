@@ -94,12 +94,12 @@ class HLstmEngine:
                          self.workspace)
 
     def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
-                num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None) -> None:
+                num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None, mix: bool = True) -> None:
         """src f32 (or uint8, quantised) [B, T_src, D]; frame_idx int32 [K] / [B,K] / None; num_frames
         int32|int64 [B] (already the *sampled* count for the student); raw_num_frames int32 [B] is the
         unsampled count (uint8 sources only).  Fills self.state and self.pred."""
         self.forward_lstm(src, frame_idx, normalize, num_frames, raw_num_frames)
-        self.classifier_forward()
+        self.classifier_forward(mix)
 
     def forward_lstm(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
                      num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None) -> None:
@@ -127,14 +127,24 @@ class HLstmEngine:
         ops.state_pack(a2.c_all[C], a2.h_all[C], b2.c_all[C], b2.h_all[C], B, H,
                        out_bf16=self.state_bf16, out_f32=self.state)
 
-    def classifier_forward(self) -> None:
-        """MoeModel on self.state_bf16 -> self.pred (video_level_models.py:423-447)."""
+    def classifier_forward(self, mix: bool = True) -> None:
+        """MoeModel on self.state_bf16 -> self.pred (video_level_models.py:423-447).  mix=False stops after
+        the two logit GEMMs (the training step applies the mixture inside its fused loss kernel)."""
         p, cfg = self.p, self.cfg
         S, V, M = cfg.state_size, cfg.vocab_size, cfg.num_mixtures
         ops.gemm(self.state_bf16, p.shadow[p.gates_w], self.B, self.ldg, S, self.G, b_mn=True)
         ops.gemm(self.state_bf16, p.shadow[p.experts_w], self.B, self.lde, S, self.E, b_mn=True,
                  bias=p.w[p.experts_b])
-        ops.moe_mix_fwd(self.G, self.ldg, self.E, self.lde, self.B, V, M, self.pred)
+        if mix:
+            ops.moe_mix_fwd(self.G, self.ldg, self.E, self.lde, self.B, V, M, self.pred)
+
+    def classifier_loss_fused(self, labels_u8, teacher_pred, ce_scale, kl_scale, ce_rows, kl_rows) -> None:
+        """Mixture + CrossEntropyLoss rows + KL(teacher||student) rows + gradients w.r.t. the logits (self.dG,
+        self.dE) in one launch; fills self.pred.  Follow with classifier_backward(None, ..., logits_done=True)."""
+        cfg = self.cfg
+        ops.moe_mix_loss(self.G, self.ldg, self.E, self.lde, teacher_pred, labels_u8, self.B, cfg.vocab_size,
+                         cfg.num_mixtures, ce_scale, kl_scale, self.pred, ce_rows, kl_rows, self.dG, self.lddg,
+                         self.dE, self.ldde)
 
     # ------------------------------------------------------------------ backward
     def _cell_bwd(self, layer: _Layer, level, cell, Kx, seq_len, dh_ext, dfinal, col, scratch):
@@ -172,11 +182,14 @@ class HLstmEngine:
         self.classifier_backward(dP, dstate_preset)
         self.lstm_backward()
 
-    def classifier_backward(self, dP: torch.Tensor, dstate_preset: bool = False) -> None:
-        """MoE backward: weight gradients into params.g, d(state) accumulated into self.dstate."""
+    def classifier_backward(self, dP: Optional[torch.Tensor], dstate_preset: bool = False,
+                            logits_done: bool = False) -> None:
+        """MoE backward: weight gradients into params.g, d(state) accumulated into self.dstate.
+        logits_done: self.dG/self.dE were already produced by classifier_loss_fused."""
         p, cfg = self.p, self.cfg
         S, V, M, B = cfg.state_size, cfg.vocab_size, cfg.num_mixtures, self.B
-        ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde)
+        if not logits_done:
+            ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde)
         if not dstate_preset:
             ops.fill_f32(self.dstate, 0.0)
         ops.gemm(self.dG, p.shadow[p.gates_w], B, S, self.ldg, self.dstate, split_k=8, accumulate=True)

@@ -138,6 +138,11 @@ def ce_kl_loss(P, PT, labels, ce_scale, kl_scale, ce_rows, kl_rows, dP):
                              ptr(dP), stream()), "evc_ce_kl_loss")
 
 
+def moe_mix_loss(G, ldg, E, lde, PT, labels, B, V, M, ce_scale, kl_scale, P, ce_rows, kl_rows, dG, lddg, dE, ldde):
+    check(lib.evc_moe_mix_loss(ptr(G), ldg, ptr(E), lde, ptr(PT), ptr(labels), B, V, M, ce_scale, kl_scale, ptr(P),
+                               ptr(ce_rows), ptr(kl_rows), ptr(dG), lddg, ptr(dE), ldde, stream()), "evc_moe_mix_loss")
+
+
 def reduce_rows(rows, scale, out):
     check(lib.evc_reduce_rows(ptr(rows), rows.numel(), scale, ptr(out), stream()), "evc_reduce_rows")
 

@@ -165,21 +165,22 @@ class TeacherStudentTrainer(_Base):
         B = self.B
         t, s = self.t_eng, self.s_eng
         # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
-        t.forward(raw, None, True, num_frames, num_frames)
+        t.forward(raw, None, True, num_frames, num_frames, mix=False)
         # student: every_n-th frame, float64 length rule (train.py:262-272,349-357)
         ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(raw, self.frame_idx, True, self.nf_student, num_frames)
-        # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term
-        ops.ce_kl_loss(t.pred, None, labels_u8, 1.0 / B, 0.0, self.rows[0], None, t.dP)
-        t.classifier_backward(t.dP)
+        s.forward(raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
+        # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term.
+        # One launch: mixture, CE rows and the gradients w.r.t. the logits.
+        t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
+        t.classifier_backward(None, logits_done=True)
         self._reduce_grads(self.teacher, self.teacher.names[8:])   # classifier gradients travel during the LSTM backward
         t.lstm_backward()
         self._reduce_grads(self.teacher, self.teacher.names[:8])
         # student loss = 2*L_REP + L_PRED + L_CE + penalty*reg (train.py:359-406); teacher tensors are
         # constants for the student's backward (F9)
         ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
-        ops.ce_kl_loss(s.pred, t.pred, labels_u8, 1.0 / B, 1.0, self.rows[1], self.rows[2], s.dP)
-        s.classifier_backward(s.dP, dstate_preset=True)
+        s.classifier_loss_fused(labels_u8, t.pred, 1.0 / B, 1.0, self.rows[1], self.rows[2])
+        s.classifier_backward(None, dstate_preset=True, logits_done=True)
         self._reduce_grads(self.student, self.student.names[8:])
         s.lstm_backward()
         self._reduce_grads(self.student, self.student.names[:8])
@@ -239,9 +240,9 @@ class StudentFinetuneTrainer(_Base):
         self._check(model_input_raw, num_frames, labels)
         B, s = self.B, self.s_eng
         ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames)
-        ops.ce_kl_loss(s.pred, None, _as_u8(labels), 1.0 / B, 0.0, self.rows[0], None, s.dP)
-        s.classifier_backward(s.dP)
+        s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
+        s.classifier_loss_fused(_as_u8(labels), None, 1.0 / B, 0.0, self.rows[0], None)
+        s.classifier_backward(None, logits_done=True)
         self._reduce_grads(self.student, self.student.names[8:])
         s.lstm_backward()
         self._reduce_grads(self.student, self.student.names[:8])

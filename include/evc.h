@@ -127,6 +127,13 @@ int evc_moe_mix_bwd(const float* G, long long ldg, const float* E, long long lde
 int evc_ce_kl_loss(const float* P, const float* PT, const unsigned char* labels, int B, int V, float ce_scale,
                    float kl_scale, float* ce_rows, float* kl_rows, float* dP, void* stream);
 
+/* The three calls above in one launch for the training step: mixture forward (P), CE rows, KL rows
+ * (PT nullable), and dG/dE = d(ce_scale*CE_row + kl_scale*KL_row)/d logits. */
+int evc_moe_mix_loss(const float* G, long long ldg, const float* E, long long lde, const float* PT,
+                     const unsigned char* labels, int B, int V, int M, float ce_scale, float kl_scale, float* P,
+                     float* ce_rows, float* kl_rows, void* dG, long long lddg, void* dE, long long ldde,
+                     void* stream);
+
 /* out[0] = scale * sum rows[0..n)  (tf.reduce_mean / reduce_sum over the batch). */
 int evc_reduce_rows(const float* rows, int n, float scale, float* out, void* stream);
 
