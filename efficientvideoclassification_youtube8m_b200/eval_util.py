@@ -130,3 +130,18 @@ class EvaluationMetrics(object):
         self.map_calculator.clear()
         self.global_ap_calculator.clear()
         self.num_examples = 0
+
+
+def format_lines(video_ids, predictions, top_k):
+    """Prediction CSV lines "<video_id>,<class> <score> ... " with the top_k classes by descending score
+    (inference_ensemble.py:63-74); the per-video selection runs on the GPU (evc_topk already returns
+    the classes in that order)."""
+    p = predictions if torch.is_tensor(predictions) else torch.as_tensor(np.asarray(predictions, dtype=np.float32))
+    if not p.is_cuda:
+        p = p.cuda()
+    idx, val, _ = ops.topk(p.to(torch.float32).contiguous(), min(top_k, p.shape[1]))
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for video_index in range(len(video_ids)):
+        vid = video_ids[video_index]
+        vid = vid.decode("utf-8") if isinstance(vid, (bytes, bytearray)) else str(vid)
+        yield vid + "," + " ".join("%i %f" % (int(c), float(s)) for c, s in zip(idx[video_index], val[video_index])) + "\n"

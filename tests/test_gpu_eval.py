@@ -142,3 +142,16 @@ def test_every_n_sweep_student_forward():
         assert np.array_equal(idx.cpu().numpy(), oi)
     with pytest.raises(ValueError):
         StudentEvaluator(params, B, every_n=7)           # 43 frames do not split into 5 chunks (F13)
+
+
+def test_format_lines_matches_reference_rule():
+    """inference_ensemble.py:63-74: top_k classes sorted by descending score, "%i %f" pairs."""
+    from efficientvideoclassification_youtube8m_b200 import eval_util
+    p = GOLD["small/predictions"]
+    ids = [("vid%02d" % i).encode() for i in range(p.shape[0])]
+    lines = list(eval_util.format_lines(ids, p, 5))
+    for b, line in enumerate(lines):
+        top = np.argpartition(p[b], -5)[-5:]
+        # equal scores: the reference keeps argpartition's arbitrary order, here the lower class comes first
+        want = sorted([(int(c), float(p[b][c])) for c in top], key=lambda q: (-q[1], q[0]))
+        assert line == ids[b].decode() + "," + " ".join("%i %f" % pair for pair in want) + "\n"
