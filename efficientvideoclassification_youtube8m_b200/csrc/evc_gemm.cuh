@@ -77,122 +77,18 @@ struct GemmCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
-  __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
-  uint4 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c);
-  r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-__device__ __forceinline__ void unpack8_bf16(const uint4& r, float* v) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(p[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void load16_f32(const float* p, float* v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 f = *reinterpret_cast<const float4*>(p + 4 * i);
-    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
-  }
-}
-__device__ __forceinline__ void store16_f32(float* p, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float* v) {
-  uint4 a = *reinterpret_cast<const uint4*>(p);
-  uint4 b = *reinterpret_cast<const uint4*>(p + 8);
-  unpack8_bf16(a, v);
-  unpack8_bf16(b, v + 8);
-}
-__device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float* v) {
-  *reinterpret_cast<uint4*>(p) = pack8_bf16(v);
-  *reinterpret_cast<uint4*>(p + 8) = pack8_bf16(v + 8);
-}
-
 // ---------------------------------------------------------------------------------------------
-// Epilogue I/O staging.  A TMEM lane is an output ROW, so an epilogue thread owns one row and 16
-// consecutive columns of it; accessing global memory that way costs 32 cache-line wavefronts per
-// warp instruction and serialises on the LSU (measured: +30 us per 98 us launch).  The epilogue
-// therefore transposes [32 rows x 16 columns] blocks through a padded per-warp shared-memory
-// area: global accesses are made by 4 (f32) / 2 (bf16) lanes per row segment with 16-byte
-// vectors, all stores of a chunk are issued back to back after ONE warp sync, and the inputs of
-// the next chunk are fetched into registers while the current chunk is being stored.
-// Block layouts in the staging area (32-bit words): f32 block = 32 rows x 16, pitch 17;
-// bf16 block = 32 rows x 8, pitch 9.  `g` = (first row of the warp, first column of the chunk).
+// Epilogue I/O staging for the LSU store path (atomics / unaligned C / the experimental persistent
+// kernel).  A TMEM lane is an output ROW, so an epilogue thread owns one row and 16 consecutive
+// columns of it; storing that way costs 32 cache-line wavefronts per warp instruction.  These
+// helpers transpose a [32 rows x 16 columns] block through a padded per-warp shared-memory area
+// so that 4 (f32) / 2 (bf16) lanes cover one row segment with 16-byte vectors.
+// Block layouts (32-bit words): f32 block = 32 rows x 16, pitch 17; bf16 block = 32 rows x 8, pitch 9.
+// `g` = (first row of the warp, first column of the chunk).
 constexpr int STG_F32 = 0;             // word offset of the f32 block
 constexpr int STG_BF16 = 32 * 17;      // word offset of bf16 block 0 (blocks are 288 words apart)
 constexpr int STG_BF16_SZ = 32 * 9;
 
-struct F32Frag { float4 x[4]; };       // what one lane moves for a 32x16 f32 block
-struct Bf16Frag { uint4 x[2]; };       // ... for a 32x16 bf16 block
-
-__device__ __forceinline__ F32Frag fetch_f32(const float* g, long long ld, int nrows, int lane) {
-  F32Frag f;
-  const int pr = lane >> 2, pc = (lane & 3) * 4;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = pr + 8 * i;
-    f.x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g != nullptr && r < nrows) f.x[i] = *reinterpret_cast<const float4*>(g + static_cast<long long>(r) * ld + pc);
-  }
-  return f;
-}
-__device__ __forceinline__ Bf16Frag fetch_bf16(const __nv_bfloat16* g, long long ld, int nrows, int lane) {
-  Bf16Frag f;
-  const int pr = lane >> 1, pc = (lane & 1) * 8;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = pr + 16 * i;
-    f.x[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (g != nullptr && r < nrows) f.x[i] = *reinterpret_cast<const uint4*>(g + static_cast<long long>(r) * ld + pc);
-  }
-  return f;
-}
-// fragment -> staging (coalesced orientation)
-__device__ __forceinline__ void stage_in_f32(float* st, const F32Frag& f, int lane) {
-  const int pr = lane >> 2, pc = (lane & 3) * 4;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float* s = st + (pr + 8 * i) * 17 + pc;
-    s[0] = f.x[i].x; s[1] = f.x[i].y; s[2] = f.x[i].z; s[3] = f.x[i].w;
-  }
-}
-__device__ __forceinline__ void stage_in_bf16(float* st, const Bf16Frag& f, int lane) {
-  uint32_t* s0 = reinterpret_cast<uint32_t*>(st);
-  const int pr = lane >> 1, pc = (lane & 1) * 4;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    uint32_t* s = s0 + (pr + 16 * i) * 9 + pc;
-    s[0] = f.x[i].x; s[1] = f.x[i].y; s[2] = f.x[i].z; s[3] = f.x[i].w;
-  }
-}
-// staging -> the 16 values of this lane's row
-__device__ __forceinline__ void stage_get_f32(const float* st, int lane, float* v) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = st[lane * 17 + j];
-}
-__device__ __forceinline__ void stage_get_bf16(const float* st, int lane, float* v) {
-  const uint32_t* s = reinterpret_cast<const uint32_t*>(st) + lane * 9;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t w = s[j];
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-    v[2 * j] = f.x;
-    v[2 * j + 1] = f.y;
-  }
-}
 // this lane's row -> staging
 __device__ __forceinline__ void stage_put_f32(float* st, int lane, const float* v) {
 #pragma unroll
