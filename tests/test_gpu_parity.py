@@ -256,3 +256,33 @@ def test_ragged_tiny_batches_and_empty_video(B):
                 assert g.norm().item() < 1e-6, n
             else:
                 assert ((g - r).norm() / den).item() < 3e-2, n
+
+
+def test_tfrecord_to_gpu_step(tmp_path):
+    """End of the input path: TFRecord shard -> TF-free reader (uint8 batches) -> training step on the GPU, equal to
+    feeding the dequantised float32 batch the reference's reader would produce."""
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200 import readers
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import TeacherStudentTrainer
+    rng = np.random.default_rng(3)
+    frames = [300, 120, 7, 45]
+    recs = []
+    for i, n in enumerate(frames):
+        f = {"rgb": rng.integers(0, 256, size=(n, 96), dtype=np.uint8),
+             "audio": rng.integers(0, 256, size=(n, 32), dtype=np.uint8)}
+        recs.append(readers.make_sequence_example(f"v{i}", sorted(rng.choice(200, 3, replace=False).tolist()), f))
+    path = str(tmp_path / "shard.tfrecord")
+    readers.write_tfrecord(path, recs)
+    rd = readers.YT8MFrameFeatureReader(num_classes=200, feature_sizes=[96, 32], feature_names=["rgb", "audio"])
+    ids, xq, y, nf = next(rd.batches([path], 4))
+    cfg = ModelConfig(**SMALL)
+    a = TeacherStudentTrainer(cfg, batch_size=4)
+    b = TeacherStudentTrainer(cfg, batch_size=4)
+    a.step(xq.cuda(), nf.cuda(), y.cuda())                                  # quantised path
+    xf = np.where(np.arange(300)[None, :, None] < nf.numpy()[:, None, None], O.dequantize(xq.numpy()), 0.0)
+    b.step(torch.from_numpy(xf.astype(np.float32)).cuda(), nf.cuda(), y.cuda())   # reference-style float batch
+    fa, fb = a.fetch(), b.fetch()
+    for k in fa:       # (the regulariser's sum of squares is accumulated with float atomics: order-dependent last bits)
+        assert abs(fa[k] - fb[k]) <= 1e-6 * abs(fb[k]), k
+    assert torch.equal(a.s_eng.pred, b.s_eng.pred) and torch.equal(a.t_eng.pred, b.t_eng.pred)
