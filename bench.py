@@ -19,6 +19,8 @@ from __future__ import annotations
 
 import argparse
 import json
+
+import numpy as np
 import os
 import subprocess
 import sys
@@ -240,6 +242,18 @@ def run_ours(args):
 
     ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
     clocks = sampler.stop()          # sampled over both timed regions (device-resident and e2e)
+
+    # same loop fed with the quantised uint8 features a tfrecord holds (readers.YT8MFrameFeatureReader):
+    # Dequantize + zero padding run inside the pack kernel, 4x fewer bytes cross PCIe
+    rngq = np.random.default_rng(1234 + rank)
+    hq = torch.from_numpy(rngq.integers(0, 256, size=x.shape, dtype=np.uint8)).pin_memory()
+    dq = [torch.empty_like(hq, device=dev) for _ in range(2)]
+    host_x[0], host_x[1], dx[0], dx[1] = hq, hq, dq[0], dq[1]
+    main.synchronize(); copy_stream.synchronize()
+    freed[0].record(main); freed[1].record(main)
+    state["i"] = 0
+    prefetch(0)
+    ms_e2e_u8 = timed(e2e_step, max(3, args.steps // 2), 2)
     h2d = host_x[0].numel() * 4 + host_nf.numel() * 4 + host_lab.numel()
     d2h = out_host.numel() * 4 + topk_host.numel() * 4
 
@@ -305,6 +319,9 @@ def run_ours(args):
             "frac_of_sustained_bf16_peak": vps * gf / 1e3 / world / peaks["bf16_tflops_sustained"],
             "e2e": {"value": e2e_vps, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
+            "e2e_uint8_input": {"value": world * B / (ms_e2e_u8 * 1e-3), "unit": "videos/s",
+                                "h2d_bytes_per_step": hq.numel() + host_nf.numel() * 4 + host_lab.numel(),
+                                "ms_per_step": ms_e2e_u8},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roof, "losses": losses,
         }
