@@ -24,6 +24,7 @@ SIGNATURES = {
     "evc_random_sequence_index": [P, P, I, I, P, P],
     "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
     "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
+    "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P],
     "evc_lstm_workspace_bytes": [I, I, I],
     "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P, L, P],
     "evc_state_pack": [P, P, P, P, I, I, P, P, P],

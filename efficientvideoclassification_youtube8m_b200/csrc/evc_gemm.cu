@@ -278,11 +278,17 @@ extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
   return (f > b ? f : b) + 256;
 }
 
-extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
-                                int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
-                                void* gates_all, void* workspace, long long workspace_bytes, void* stream_) {
+// Steps [t_begin, t_end) of the same layer: lets the host interleave the two cells of a MultiRNNCell on two
+// streams (cell 1 step t only needs cell 0 step t), so that the SMs one kernel leaves idle in its last round
+// over the tiles are taken by the other cell's kernel.
+extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, int Kx, const void* W,
+                                      const float* bias, int rows, int H, int T, int t_begin, int t_end,
+                                      const int* seq_len, void* h_all, float* c_all, void* gates_all,
+                                      void* workspace, long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: empty problem");
+  if (t_begin < 0 || t_end > T || t_begin >= t_end) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: bad step range");
+  const bool whole = (t_begin == 0 && t_end == T);
   if (H % 64 != 0 || Kx % 64 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: H and Kx must be multiples of 64");
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h_all);
@@ -300,7 +306,7 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
       persistent = e ? atoi(e) : 0;
     }
     const int tiles = ceil_div(rows, BM) * (4 * H / 256);
-    if (persistent && workspace != nullptr && T >= 2 && tiles <= num_sms() && H % 64 == 0) {
+    if (persistent && whole && workspace != nullptr && T >= 2 && tiles <= num_sms() && H % 64 == 0) {
       int S = num_sms() / tiles;
       if (S > 8) S = 8;
       while (S > 1 && (Kx + H) / BK / S < 8) --S;
@@ -353,7 +359,7 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
     // the slabs and applies bias / gates / state update / length mask.
     float* part = static_cast<float*>(workspace);
     const long long slab = static_cast<long long>(rows) * 4 * H;
-    for (int t = 0; t < T; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       const int K = Kx + (t == 0 ? 0 : H);          // h_{-1} = 0: skip the recurrent half at t = 0
       const int want = pick_split(ceil_div(rows, BM) * (4 * H / 256), K / BK);
       if (static_cast<long long>(want) * slab * 4 > workspace_bytes)
@@ -373,7 +379,7 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
   CUtensorMap tb;
   rc = make_tmap_b(&tb, W, 1, 4LL * H, 4 * H, Kx + H, 256, cs);
   if (rc) return rc;
-  for (int t = 0; t < T; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     CUtensorMap ta1, ta2;
     rc = make_tmap_a(&ta1, xb + t * x_step_stride, 0, Kx, rows, Kx);
     if (rc) return rc;
@@ -400,6 +406,13 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
     if (rc) return rc;
   }
   return EVC_OK;
+}
+
+extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
+                                int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
+                                void* gates_all, void* workspace, long long workspace_bytes, void* stream_) {
+  return evc_lstm_seq_fwd_steps(x, x_step_stride, Kx, W, bias, rows, H, T, 0, T, seq_len, h_all, c_all, gates_all,
+                                workspace, workspace_bytes, stream_);
 }
 
 // ------------------------------------------------------------------ BasicLSTM layer, backward over T steps

@@ -21,6 +21,7 @@ R1 = C*B rows at the lower level):
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -29,6 +30,15 @@ from . import ops
 from .params import HLstmParams
 
 BF16 = torch.bfloat16
+
+# Stream-level overlap (bit mask, EVC_OVERLAP): 1 = the student model on its own stream (steps.py),
+# 2 = the two cells of RNN_L1 interleaved step by step on two streams, 4 = weight-gradient GEMMs on a
+# side stream next to the backward recurrence of the layer below.
+OVERLAP_STUDENT, OVERLAP_CELLS, OVERLAP_WGRAD = 1, 2, 4
+
+
+def overlap_mode() -> int:
+    return int(os.environ.get("EVC_OVERLAP", "7"))
 
 
 class _Layer:
@@ -52,6 +62,9 @@ class HLstmEngine:
         self.B, self.K, self.C = batch, num_frames_in, num_chunks
         self.ell = num_frames_in // num_chunks
         self.training = training
+        self.overlap = overlap_mode()
+        self._side: Optional[torch.cuda.Stream] = None
+        self._events = []
         dev = params.device
         H, D, V, M, S = cfg.lstm_cells, cfg.feature_size, cfg.vocab_size, cfg.num_mixtures, cfg.state_size
         self.R1 = self.C * self.B
@@ -87,11 +100,21 @@ class HLstmEngine:
                            torch.empty(B, H, dtype=torch.float32, device=dev))
 
     # ------------------------------------------------------------------ forward
-    def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len):
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.p.device, priority=int(os.environ.get("EVC_PRIO_SIDE", "0")))
+        return self._side
+
+    def _event(self, i: int) -> torch.cuda.Event:
+        while len(self._events) <= i:
+            self._events.append(torch.cuda.Event())
+        return self._events[i]
+
+    def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len, t_begin=0, t_end=None):
         p = self.p
         ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
                          layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates,
-                         self.workspace)
+                         self.workspace, t_begin, t_end)
 
     def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
                 num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None, mix: bool = True) -> None:
@@ -118,8 +141,21 @@ class HLstmEngine:
             ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x)
         ops.lstm_lengths(num_frames, C, ell, self.len_l1, self.len_l2)
         a, b = self.l1
-        self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1)
-        self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1)
+        if (self.overlap & OVERLAP_CELLS) and R1 > 1024:
+            # MultiRNNCell wavefront: cell 1 step t next to cell 0 step t+1 (fused-epilogue steps only: the
+            # split-K path of the small-row steps shares one scratch buffer)
+            main, side = torch.cuda.current_stream(), self._side_stream()
+            for t in range(ell):
+                self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1, t, t + 1)
+                ev = self._event(t)
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1, t, t + 1)
+            main.wait_stream(side)
+        else:
+            self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1)
+            self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1)
         ops.state_pack(a.c_all[ell], a.h_all[ell], b.c_all[ell], b.h_all[ell], R1, H, out_bf16=self.l2_in)
         a2, b2 = self.l2
         self._cell_fwd(a2, self.l2_in, B * S, S, 1, 0, self.len_l2)
@@ -207,16 +243,36 @@ class HLstmEngine:
         B, R1, ell, C = self.B, self.R1, self.ell, self.C
         # ---- RNN_L2 (cell 1 first: its input gradient feeds cell 0)
         a2, b2 = self.l2
+        a, b = self.l1
+        if self.overlap & OVERLAP_WGRAD:
+            # dz of a cell is final once its recurrence is done: its weight-gradient GEMMs (tensor-bound, no
+            # dependants until the optimizer) run on the side stream next to the latency-bound recurrence
+            # of the cell below
+            main, side = torch.cuda.current_stream(), self._side_stream()
+
+            def wgrad_aside(i, *args):
+                ev = self._event(i)
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self._cell_wgrad(*args)
+        else:
+            main = side = None
+
+            def wgrad_aside(i, *args):
+                self._cell_wgrad(*args)
+        # ---- RNN_L2 (cell 1 first: its input gradient feeds cell 0)
         self._cell_bwd(b2, 1, 1, H, self.len_l2, None, self.dstate, 2 * H, self.scr_l2)
-        self._cell_wgrad(b2, 1, 1, a2.h_all[1:].view(-1, H), H)
+        wgrad_aside(0, b2, 1, 1, a2.h_all[1:].view(-1, H), H)
         self._cell_dx(b2, 1, 1, H, self.dx_l2)
         self._cell_bwd(a2, 1, 0, S, self.len_l2, self.dx_l2, self.dstate, 0, self.scr_l2)
-        self._cell_wgrad(a2, 1, 0, self.l2_in.view(-1, S), S)
+        wgrad_aside(1, a2, 1, 0, self.l2_in.view(-1, S), S)
         self._cell_dx(a2, 1, 0, S, self.dl2_in)
         # ---- RNN_L1: final-state gradient of chunk i = gradient of RNN_L2's input at step i
-        a, b = self.l1
         self._cell_bwd(b, 0, 1, H, self.len_l1, None, self.dl2_in, 2 * H, self.scr_l1)
-        self._cell_wgrad(b, 0, 1, a.h_all[1:].view(-1, H), H)
+        wgrad_aside(2, b, 0, 1, a.h_all[1:].view(-1, H), H)
         self._cell_dx(b, 0, 1, H, self.dx_l1)
         self._cell_bwd(a, 0, 0, D, self.len_l1, self.dx_l1, self.dl2_in, 0, self.scr_l1)
         self._cell_wgrad(a, 0, 0, self.x.view(-1, D), D)
+        if side is not None:
+            main.wait_stream(side)

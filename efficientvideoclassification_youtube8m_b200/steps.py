@@ -14,13 +14,14 @@ flat gradient buffer before the per-variable clip + Adam.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist
 
 from . import ops
-from .engine import HLstmEngine
+from .engine import OVERLAP_STUDENT, HLstmEngine, overlap_mode
 from .params import HLstmParams, ModelConfig
 
 MAX_FRAMES = 300  # train.py:262
@@ -160,8 +161,53 @@ class TeacherStudentTrainer(_Base):
         dev, B = self.device, batch_size
         self.rows = torch.zeros(4, B, dtype=torch.float32, device=dev)   # CE_T, CE_S, KL, REP rows
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)    # CE_T, CE_S, L_PRED, L_REP
+        # The student only needs the teacher's final state and predictions (constants of its loss, F9): its
+        # forward, backward and optimizer pass run on a second stream, so its latency-bound small-row
+        # launches fill the SMs the teacher's kernels leave idle and the teacher's HBM-bound clip+Adam
+        # runs next to the student's backward GEMMs.
+        self.student_stream = (torch.cuda.Stream(device=self.device,
+                                                 priority=int(os.environ.get("EVC_PRIO_STUDENT", "0")))
+                               if (overlap_mode() & OVERLAP_STUDENT) and self.device.type == "cuda" else None)
+        self._teacher_ready = torch.cuda.Event() if self.student_stream is not None else None
+
+    def _forward_backward_two_streams(self, raw, num_frames, labels_u8):
+        B = self.B
+        t, s = self.t_eng, self.s_eng
+        main, side = torch.cuda.current_stream(), self.student_stream
+        side.wait_stream(main)                       # the batch (and last step's weights) are ready
+        with torch.cuda.stream(side):
+            ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
+            s.forward(raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
+        t.forward(raw, None, True, num_frames, num_frames, mix=False)
+        t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
+        self._teacher_ready.record(main)             # t.state and t.pred are final
+        with torch.cuda.stream(side):
+            side.wait_event(self._teacher_ready)
+            ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
+            s.classifier_loss_fused(labels_u8, t.pred, 1.0 / B, 1.0, self.rows[1], self.rows[2])
+            s.classifier_backward(None, dstate_preset=True, logits_done=True)
+            self._reduce_grads(self.student, self.student.names[8:])
+        t.classifier_backward(None, logits_done=True)
+        self._reduce_grads(self.teacher, self.teacher.names[8:])
+        t.lstm_backward()
+        self._reduce_grads(self.teacher, self.teacher.names[:8])
+        ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
+        with torch.cuda.stream(side):
+            s.lstm_backward()
+            self._reduce_grads(self.student, self.student.names[:8])
+            ops.reduce_rows(self.rows[1], 1.0 / B, self.losses[1:2])
+            ops.reduce_rows(self.rows[2], 1.0, self.losses[2:3])
+            ops.reduce_rows(self.rows[3], 1.0 / B, self.losses[3:4])
 
     def forward_backward(self, raw, num_frames, labels_u8):
+        """Losses and gradients of both models (complete on the current stream when this returns)."""
+        self._forward_backward(raw, num_frames, labels_u8)
+        if self.student_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.student_stream)
+
+    def _forward_backward(self, raw, num_frames, labels_u8):
+        if self.student_stream is not None:
+            return self._forward_backward_two_streams(raw, num_frames, labels_u8)
         B = self.B
         t, s = self.t_eng, self.s_eng
         # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
@@ -190,19 +236,23 @@ class TeacherStudentTrainer(_Base):
         ops.reduce_rows(self.rows[3], 1.0 / B, self.losses[3:4])
 
     def apply_gradients(self):
+        # the teacher's optimizer pass runs while the student's last gradient slice is still on the wire
+        # (one stream) or while the student's backward is still running (two streams)
         self._apply(self.teacher)
-        self._apply(self.student)
+        if self.student_stream is not None:
+            with torch.cuda.stream(self.student_stream):
+                self._apply(self.student)
+            torch.cuda.current_stream().wait_stream(self.student_stream)
+        else:
+            self._apply(self.student)
         self._finish_gathers()
 
     def step(self, model_input_raw, num_frames, labels) -> None:
         """One iteration = both train ops (global_step += 2).  Asynchronous; read
         results with :meth:`fetch`."""
         self._check(model_input_raw, num_frames, labels)
-        self.forward_backward(model_input_raw, num_frames, _as_u8(labels))
-        # the teacher's optimizer pass runs while the student's last gradient slice is still on the wire
-        self._apply(self.teacher)
-        self._apply(self.student)
-        self._finish_gathers()
+        self._forward_backward(model_input_raw, num_frames, _as_u8(labels))
+        self.apply_gradients()
         self.global_step += 2
 
     def fetch(self) -> Dict[str, float]:

@@ -88,6 +88,12 @@ int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
 int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias, int rows,
                      int H, int T, const int* seq_len, void* h_all, float* c_all, void* gates_all, void* workspace,
                      long long workspace_bytes, void* stream);
+/* Steps [t_begin, t_end) of evc_lstm_seq_fwd (same buffers, same arithmetic).  cell 1 of a MultiRNNCell
+ * only needs cell 0's output of the same step (tf.nn.dynamic_rnn evaluates the stack step by step,
+ * frame_level_models.py:221-249), so the host interleaves the two cells' steps on two streams. */
+int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
+                           int rows, int H, int T, int t_begin, int t_end, const int* seq_len, void* h_all,
+                           float* c_all, void* gates_all, void* workspace, long long workspace_bytes, void* stream);
 /* Scratch needed by evc_lstm_seq_fwd / evc_lstm_seq_bwd for one cell (split-K partial slabs).  With a
  * workspace, steps with <= 1024 rows (RNN_L2, the student) run as a split-K GEMM over all SMs + a
  * full-occupancy cell kernel; without one (NULL) every step uses the fused-epilogue kernel. */
