@@ -64,6 +64,8 @@ def _load(path: str = LIB_PATH):
 
 
 lib = _load()
+if os.environ.get("EVC_DEBUG"):          # profiling experiments only (ablation bits of evc_debug_set)
+    lib.evc_debug_set(int(os.environ["EVC_DEBUG"]))
 
 
 def check(rc: int, what: str = "") -> None:

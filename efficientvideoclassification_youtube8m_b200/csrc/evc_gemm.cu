@@ -132,7 +132,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   const int clusters = work < max_clusters ? work : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CS);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -470,6 +470,7 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     g.kb_total = last ? 0 : (4 * H) / BK;
     g.kb_a1 = g.kb_total;
     g.kb_per_split = g.kb_total > 0 ? g.kb_total : 1;
+    g.debug = g_debug;
     g.t = t; g.seq_len = seq_len;
     g.gates = const_cast<__nv_bfloat16*>(gb + t * RH * 4);
     g.c_prev = (t == 0) ? nullptr : c_all + t * RH;

@@ -26,6 +26,15 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 4;   // one per TMEM lane quarter
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+// The fused BasicLSTM forward epilogue executes ~7k instructions per tile and warp (transposition through
+// shared memory, 5 transcendentals per unit, vector I/O); with one warp per scheduler it issues one
+// instruction every 4 cycles (ncu: issue active 25 %) and takes longer per tile than the main loop.  It
+// therefore runs with TWO warps per TMEM lane quarter (each owns 32 of the tile's 64 units), which share
+// the scheduler and hide each other's latencies; the other epilogues keep one.
+template <int EPI> struct EpiCfg {
+  static constexpr int WARPS = (EPI == EPI_LSTM_FWD) ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * WARPS;
+};
 
 struct GemmArgs {
   int M, N;            // output extent (rows, columns) used for masking
@@ -72,6 +81,7 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   // per epilogue warp 8 KB (1024-byte aligned): two 32x32-word TMA store boxes (plain GEMM), or the
   // accumulator transposition area of the LSTM epilogues (4 XOR-swizzled 32x16 blocks / one 32x33 block)
+  // (the 8 warps of the LSTM forward epilogue get half of it each: 2 gates x 32 rows x 16 units per pass)
   static constexpr int EPI_STAGE_WORDS = 2048;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_WORDS * 4 + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -129,7 +139,7 @@ __device__ __forceinline__ void flush_bf16(const float* st, __nv_bfloat16* g, lo
 // block, each loads 1/CS of the B tile and multicasts it to all of them (L2 -> SM operand
 // traffic per CTA drops from A+B to A+B/CS; the kernel is L2-bandwidth bound without it).
 template <int A_MN, int B_MN, int BN, int EPI, int CS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
@@ -161,7 +171,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
     for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);
+      mbar_init(&tempty_bar[i], EpiCfg<EPI>::WARPS);
     }
     fence_barrier_init();
   }
@@ -173,7 +183,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_ptr;
   // everything above touched only this kernel's own shared memory / TMEM: it may overlap the tail of the
   // previous kernel; global memory is first read below
-  pdl_launch_dependents();
+  // The dependent grid is released late: when every CTA has started its LAST work item (trigger below, in the
+  // producer).  Released at this point instead, a dependent GEMM's CTAs would take each SM the moment this
+  // grid's CTA leaves it and sit in griddepcontrol.wait until the whole grid has drained -- SMs that a ready
+  // kernel of another stream (the other LSTM cell, the student model) can use for real work.
+  if (args.debug & 1024) pdl_launch_dependents();   // experiment: early release (the single-stream optimum)
   pdl_wait();
 
   // work item = CS M-adjacent tiles (one per CTA of the cluster); tiles past tiles_m are all-OOB dummies
@@ -185,7 +199,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool released = (args.debug & 1024) != 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
+        if (!released && w + num_clusters >= num_work) {   // last work item of this CTA
+          pdl_launch_dependents();
+          released = true;
+        }
         const int wt = w % (tiles_mc * args.tiles_n);
         const int m_blk = (args.n_fastest ? wt / args.tiles_n : wt % tiles_mc) * CS + cta_rank;
         const int n_blk = args.n_fastest ? wt % args.tiles_n : wt / tiles_mc;
@@ -264,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   } else {
     // ===================================================== epilogue warps
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    float* stage = epi_stage_base + (warp - 2) * Cfg::EPI_STAGE_WORDS;
+    float* stage = epi_stage_base + (warp - 2) * (Cfg::EPI_STAGE_WORDS * EPI_WARPS / EpiCfg<EPI>::WARPS);
     float* st_f = stage + STG_F32;
     float* st_b0 = stage + STG_BF16;
     int it = 0;
@@ -415,31 +434,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         // accumulators are transposed through shared memory (one TMEM lane = one row), then every
         // lane owns 4 consecutive units of a row: all global accesses are 8/16-byte vectors with
         // 4 lanes covering one 64-byte row segment (8 row segments per warp instruction).
+        // Two warps share a TMEM lane quarter: warps 2..5 take units [0,32) of the tile, warps 6..9 units
+        // [32,64).  The transposition runs in two passes of two gates (i,j then f,o) over a 4 KB area.
         const int H = args.H;
         const int pr = lane >> 2, pc = (lane & 3) * 4;
+        const int cu_begin = ((warp - 2) >> 2) * 32;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int cu = 0; cu < 64; cu += 16) {
-          {
-            uint32_t ri[16], rj[16], rf[16], ro[16];
-            tmem_ld16(taddr + 0 * 64 + cu, ri);
-            tmem_ld16(taddr + 1 * 64 + cu, rj);
-            tmem_ld16(taddr + 2 * 64 + cu, rf);
-            tmem_ld16(taddr + 3 * 64 + cu, ro);
-            tmem_ld_wait();
-            if (args.debug == 1) continue;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {                   // [gate][row][col ^ (row & 15)]
-              const int sj = lane * 16 + (j ^ (lane & 15));
-              stage[0 * 512 + sj] = __uint_as_float(ri[j]);
-              stage[1 * 512 + sj] = __uint_as_float(rj[j]);
-              stage[2 * 512 + sj] = __uint_as_float(rf[j]);
-              stage[3 * 512 + sj] = __uint_as_float(ro[j]);
-            }
-          }
-          __syncwarp();
+        for (int cu = cu_begin; cu < cu_begin + 32; cu += 16) {
           const int u = n_blk * 64 + cu + pc;               // first of this lane's 4 units
+          // independent global loads first: bias, previous cell state, sequence lengths
           const float4 bi = __ldg(reinterpret_cast<const float4*>(args.bias + 0 * H + u));
           const float4 bj = __ldg(reinterpret_cast<const float4*>(args.bias + 1 * H + u));
           const float4 bf = __ldg(reinterpret_cast<const float4*>(args.bias + 2 * H + u));
@@ -449,30 +454,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           float4 cpv[4];
           bool okr[4], liver[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {                     // issue all independent loads first
+          for (int i = 0; i < 4; ++i) {
             const int r = row0 + pr + 8 * i;
             okr[i] = r < args.M;
             liver[i] = okr[i] && (args.t < __ldg(args.seq_len + (okr[i] ? r : 0)));
             cpv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (okr[i] && args.c_prev != nullptr && !(args.debug & 4))
+            if (okr[i] && args.c_prev != nullptr)
               cpv[i] = *reinterpret_cast<const float4*>(args.c_prev + static_cast<long long>(r) * H + u);
           }
+          // ---- pass 1: input gate i and candidate j
+          {
+            uint32_t ri[16], rj[16];
+            tmem_ld16(taddr + 0 * 64 + cu, ri);
+            tmem_ld16(taddr + 1 * 64 + cu, rj);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {                   // [gate][row][col ^ (row & 15)]
+              const int sj = lane * 16 + (j ^ (lane & 15));
+              stage[0 * 512 + sj] = __uint_as_float(ri[j]);
+              stage[1 * 512 + sj] = __uint_as_float(rj[j]);
+            }
+          }
+          __syncwarp();
+          float gi[4][4], gj[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = pr + 8 * i;
+            const float* sp = stage + rl * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int sk = (pc + k) ^ (rl & 15);
+              gi[i][k] = sigmoid_f(sp[0 * 512 + sk] + bia[0][k]);
+              gj[i][k] = tanh_f(sp[1 * 512 + sk] + bia[1][k]);
+            }
+          }
+          __syncwarp();                                     // staging is overwritten by pass 2
+          // ---- pass 2: forget gate f and output gate o
+          {
+            uint32_t rf[16], ro[16];
+            tmem_ld16(taddr + 2 * 64 + cu, rf);
+            tmem_ld16(taddr + 3 * 64 + cu, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int sj = lane * 16 + (j ^ (lane & 15));
+              stage[0 * 512 + sj] = __uint_as_float(rf[j]);
+              stage[1 * 512 + sj] = __uint_as_float(ro[j]);
+            }
+          }
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = pr + 8 * i;
             const int r = row0 + rl;
             const float* sp = stage + rl * 16;
             const float cp[4] = {cpv[i].x, cpv[i].y, cpv[i].z, cpv[i].w};
-            float cn[4], hn[4], g4[4][4];
+            float cn[4], hn[4], gf[4], go[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int sk = (pc + k) ^ (rl & 15);
-              g4[0][k] = sigmoid_f(sp[0 * 512 + sk] + bia[0][k]);
-              g4[1][k] = tanh_f(sp[1 * 512 + sk] + bia[1][k]);
-              g4[2][k] = sigmoid_f(sp[2 * 512 + sk] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
-              g4[3][k] = sigmoid_f(sp[3 * 512 + sk] + bia[3][k]);
-              cn[k] = cp[k] * g4[2][k] + g4[0][k] * g4[1][k];
-              hn[k] = tanh_f(cn[k]) * g4[3][k];
+              gf[k] = sigmoid_f(sp[0 * 512 + sk] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
+              go[k] = sigmoid_f(sp[1 * 512 + sk] + bia[3][k]);
+              cn[k] = cp[k] * gf[k] + gi[i][k] * gj[i][k];
+              hn[k] = tanh_f(cn[k]) * go[k];
             }
             if (!okr[i]) continue;
             const long long off = static_cast<long long>(r) * H + u;
@@ -484,18 +528,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               *reinterpret_cast<uint2*>(args.h_out + off) = hp;
               continue;
             }
-            if (args.debug == 2) {
-              if (cn[0] + hn[1] + g4[0][2] + g4[1][3] + g4[2][0] + g4[3][1] == 123.456f) args.c_out[0] = cn[0];
-              continue;
-            }
-            if (!(args.debug & 16)) {
-              *reinterpret_cast<float4*>(args.c_out + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-              __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
-              *reinterpret_cast<uint2*>(args.h_out + off) =
-                  make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-            }
-            if (args.gates != nullptr && !(args.debug & 8)) {
+            *reinterpret_cast<float4*>(args.c_out + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
+            *reinterpret_cast<uint2*>(args.h_out + off) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+            if (args.gates != nullptr) {
               __nv_bfloat16* gp = args.gates + static_cast<long long>(r) * 4 * H + u;
+              const float* g4[4] = {gi[i], gj[i], gf, go};
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 __nv_bfloat162 a01 = __floats2bfloat162_rn(g4[g][0], g4[g][1]);

@@ -110,11 +110,12 @@ class HLstmEngine:
             self._events.append(torch.cuda.Event())
         return self._events[i]
 
-    def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len, t_begin=0, t_end=None):
+    def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len, t_begin=0, t_end=None,
+                  cuda_stream=None):
         p = self.p
         ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
                          layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates,
-                         self.workspace, t_begin, t_end)
+                         self.workspace, t_begin, t_end, cuda_stream)
 
     def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
                 num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None, mix: bool = True) -> None:
@@ -145,13 +146,13 @@ class HLstmEngine:
             # MultiRNNCell wavefront: cell 1 step t next to cell 0 step t+1 (fused-epilogue steps only: the
             # split-K path of the small-row steps shares one scratch buffer)
             main, side = torch.cuda.current_stream(), self._side_stream()
+            h0_seq = a.h_all[1:]
             for t in range(ell):
-                self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1, t, t + 1)
+                self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1, t, t + 1, main.cuda_stream)
                 ev = self._event(t)
                 ev.record(main)
                 side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1, t, t + 1)
+                self._cell_fwd(b, h0_seq, R1 * H, H, 0, 1, self.len_l1, t, t + 1, side.cuda_stream)
             main.wait_stream(side)
         else:
             self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1)

@@ -95,13 +95,14 @@ def lstm_workspace_bytes(rows, H, Kx):
 
 
 def lstm_seq_fwd(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_all, gates_all, workspace=None,
-                 t_begin=0, t_end=None):
-    """All T steps of one BasicLSTMCell layer, or only steps [t_begin, t_end)."""
+                 t_begin=0, t_end=None, cuda_stream=None):
+    """All T steps of one BasicLSTMCell layer, or only steps [t_begin, t_end); on the current stream or on
+    the raw `cuda_stream` handle."""
     t_end = T if t_end is None else t_end
     check(lib.evc_lstm_seq_fwd_steps(ptr(x), x_step_stride, Kx, ptr(W), ptr(bias), rows, H, T, t_begin, t_end,
                                      ptr(seq_len), ptr(h_all), ptr(c_all), ptr(gates_all), ptr(workspace),
                                      workspace.numel() * workspace.element_size() if workspace is not None else 0,
-                                     stream()), "evc_lstm_seq_fwd_steps")
+                                     stream() if cuda_stream is None else cuda_stream), "evc_lstm_seq_fwd_steps")
 
 
 def lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates_all, c_all, dh_ext_all, dh_final, ld_dh_final, dc_final,

@@ -175,10 +175,12 @@ class TeacherStudentTrainer(_Base):
         t, s = self.t_eng, self.s_eng
         main, side = torch.cuda.current_stream(), self.student_stream
         side.wait_stream(main)                       # the batch (and last step's weights) are ready
+        # (the teacher's launches are issued first: when the host starts a step on an idle device, its large
+        # kernels should be in the queue before the student's small ones)
+        t.forward(raw, None, True, num_frames, num_frames, mix=False)
         with torch.cuda.stream(side):
             ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
             s.forward(raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
-        t.forward(raw, None, True, num_frames, num_frames, mix=False)
         t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
         self._teacher_ready.record(main)             # t.state and t.pred are final
         with torch.cuda.stream(side):
