@@ -437,8 +437,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         // Two warps share a TMEM lane quarter: warps 2..5 take units [0,32) of the tile, warps 6..9 units
         // [32,64).  The transposition runs in two passes of two gates (i,j then f,o) over a 4 KB area.
         const int H = args.H;
-        const int pr = lane >> 2, pc = (lane & 3) * 4;
+        const int pr = lane >> 2, pc = (lane & 3) * 4;   // this lane: rows pr + 8i, units pc .. pc+3 of the chunk
         const int cu_begin = ((warp - 2) >> 2) * 32;
+        uint4* st4 = reinterpret_cast<uint4*>(stage);
+        const float4* ld4 = reinterpret_cast<const float4*>(stage);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -468,11 +470,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tmem_ld16(taddr + 0 * 64 + cu, ri);
             tmem_ld16(taddr + 1 * 64 + cu, rj);
             tmem_ld_wait();
+            // staging layout: [gate][row][4 x 16 bytes], the 16-byte slot index XOR (row >> 1) & 3: the
+            // row-per-lane writes and the (8 rows x 4 slots)-per-warp reads are both conflict-free 128-bit
+            // accesses (a quarter warp covers all 8 bank groups)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {                   // [gate][row][col ^ (row & 15)]
-              const int sj = lane * 16 + (j ^ (lane & 15));
-              stage[0 * 512 + sj] = __uint_as_float(ri[j]);
-              stage[1 * 512 + sj] = __uint_as_float(rj[j]);
+            for (int qd = 0; qd < 4; ++qd) {
+              const int slot = lane * 4 + (qd ^ ((lane >> 1) & 3));
+              st4[0 * 128 + slot] = make_uint4(ri[4 * qd], ri[4 * qd + 1], ri[4 * qd + 2], ri[4 * qd + 3]);
+              st4[1 * 128 + slot] = make_uint4(rj[4 * qd], rj[4 * qd + 1], rj[4 * qd + 2], rj[4 * qd + 3]);
             }
           }
           __syncwarp();
@@ -480,12 +485,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = pr + 8 * i;
-            const float* sp = stage + rl * 16;
+            const int slot = rl * 4 + ((lane & 3) ^ ((rl >> 1) & 3));
+            const float4 vi = ld4[0 * 128 + slot], vj = ld4[1 * 128 + slot];
+            const float pi[4] = {vi.x, vi.y, vi.z, vi.w}, pj[4] = {vj.x, vj.y, vj.z, vj.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int sk = (pc + k) ^ (rl & 15);
-              gi[i][k] = sigmoid_f(sp[0 * 512 + sk] + bia[0][k]);
-              gj[i][k] = tanh_f(sp[1 * 512 + sk] + bia[1][k]);
+              gi[i][k] = sigmoid_f(pi[k] + bia[0][k]);
+              gj[i][k] = tanh_f(pj[k] + bia[1][k]);
             }
           }
           __syncwarp();                                     // staging is overwritten by pass 2
@@ -496,10 +502,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tmem_ld16(taddr + 3 * 64 + cu, ro);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int sj = lane * 16 + (j ^ (lane & 15));
-              stage[0 * 512 + sj] = __uint_as_float(rf[j]);
-              stage[1 * 512 + sj] = __uint_as_float(ro[j]);
+            for (int qd = 0; qd < 4; ++qd) {
+              const int slot = lane * 4 + (qd ^ ((lane >> 1) & 3));
+              st4[0 * 128 + slot] = make_uint4(rf[4 * qd], rf[4 * qd + 1], rf[4 * qd + 2], rf[4 * qd + 3]);
+              st4[1 * 128 + slot] = make_uint4(ro[4 * qd], ro[4 * qd + 1], ro[4 * qd + 2], ro[4 * qd + 3]);
             }
           }
           __syncwarp();
@@ -507,14 +513,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           for (int i = 0; i < 4; ++i) {
             const int rl = pr + 8 * i;
             const int r = row0 + rl;
-            const float* sp = stage + rl * 16;
+            const int slot = rl * 4 + ((lane & 3) ^ ((rl >> 1) & 3));
+            const float4 vf = ld4[0 * 128 + slot], vo = ld4[1 * 128 + slot];
+            const float pf[4] = {vf.x, vf.y, vf.z, vf.w}, po[4] = {vo.x, vo.y, vo.z, vo.w};
             const float cp[4] = {cpv[i].x, cpv[i].y, cpv[i].z, cpv[i].w};
             float cn[4], hn[4], gf[4], go[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int sk = (pc + k) ^ (rl & 15);
-              gf[k] = sigmoid_f(sp[0 * 512 + sk] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
-              go[k] = sigmoid_f(sp[1 * 512 + sk] + bia[3][k]);
+              gf[k] = sigmoid_f(pf[k] + bia[2][k] + 1.0f);   // forget_bias = 1.0 added at use
+              go[k] = sigmoid_f(po[k] + bia[3][k]);
               cn[k] = cp[k] * gf[k] + gi[i][k] * gj[i][k];
               hn[k] = tanh_f(cn[k]) * go[k];
             }
