@@ -433,6 +433,7 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     // kernel.  Measured faster than the fused epilogue at every row count: the cell backward moves
     // 36 B per element, which 4 epilogue warps per SM cannot keep in flight behind a 4096-deep GEMM.
     float* part = static_cast<float*>(workspace);
+    // (128x128 tiles without split-K -- twice the tiles, half the slab traffic -- measured 2 % slower per step)
     const int want = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
     if (static_cast<long long>(want) * RH * 4 > workspace_bytes)
       return set_error(EVC_ERR_ARG, "lstm_seq_bwd: workspace too small (evc_lstm_workspace_bytes)");

@@ -33,11 +33,15 @@ BF16 = torch.bfloat16
 
 # Stream-level overlap (bit mask, EVC_OVERLAP): 1 = the student model on its own stream (steps.py),
 # 2 = the two cells of RNN_L1 interleaved step by step on two streams, 4 = weight-gradient GEMMs on a
-# side stream next to the backward recurrence of the layer below.
-OVERLAP_STUDENT, OVERLAP_CELLS, OVERLAP_WGRAD = 1, 2, 4
+# side stream next to the backward recurrence of the layer below, 8 = (one GPU) clip+Adam of the classifier
+# variables on an optimizer stream next to the LSTM backward.
+OVERLAP_STUDENT, OVERLAP_CELLS, OVERLAP_WGRAD, OVERLAP_OPTIMIZER, OVERLAP_CELLS_L2 = 1, 2, 4, 8, 16
 
 
 def overlap_mode() -> int:
+    """Default 7.  Bit 8 measured no gain on the joint step and -4 % on the cfg #4 fine-tune step (the
+    optimizer's HBM traffic slows the power-capped GEMMs it runs next to); bit 16 = the same interleaving
+    for RNN_L2's small-row steps (second split-K scratch buffer)."""
     return int(os.environ.get("EVC_OVERLAP", "7"))
 
 
@@ -85,6 +89,8 @@ class HLstmEngine:
         ws = max(ops.lstm_workspace_bytes(R1, H, D), ops.lstm_workspace_bytes(R1, H, H),
                  ops.lstm_workspace_bytes(B, H, S), ops.lstm_workspace_bytes(B, H, H))
         self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
+        self.workspace2 = (torch.empty(ops.lstm_workspace_bytes(B, H, H), dtype=torch.uint8, device=dev)
+                           if self.overlap & OVERLAP_CELLS_L2 else None)
         if training:
             self.lddg, self.ldde = ops.pad8(self.ldg, 64), ops.pad8(self.lde, 64)
             self.dG = torch.zeros(B, self.lddg, dtype=BF16, device=dev)
@@ -111,11 +117,24 @@ class HLstmEngine:
         return self._events[i]
 
     def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len, t_begin=0, t_end=None,
-                  cuda_stream=None):
+                  cuda_stream=None, workspace=None):
         p = self.p
         ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
                          layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates,
-                         self.workspace, t_begin, t_end, cuda_stream)
+                         self.workspace if workspace is None else workspace, t_begin, t_end, cuda_stream)
+
+    def _cells_interleaved(self, a: _Layer, b: _Layer, x, x_stride, Kx, level, seq_len, workspace_b=None):
+        """MultiRNNCell wavefront: cell 1 step t (side stream) next to cell 0 step t+1 (current stream)."""
+        main, side = torch.cuda.current_stream(), self._side_stream()
+        h0_seq = a.h_all[1:]
+        H = a.H
+        for t in range(a.T):
+            self._cell_fwd(a, x, x_stride, Kx, level, 0, seq_len, t, t + 1, main.cuda_stream)
+            ev = self._event(t)
+            ev.record(main)
+            side.wait_event(ev)
+            self._cell_fwd(b, h0_seq, a.rows * H, H, level, 1, seq_len, t, t + 1, side.cuda_stream, workspace_b)
+        main.wait_stream(side)
 
     def forward(self, src: torch.Tensor, frame_idx: Optional[torch.Tensor], normalize: bool,
                 num_frames: torch.Tensor, raw_num_frames: Optional[torch.Tensor] = None, mix: bool = True) -> None:
@@ -145,22 +164,17 @@ class HLstmEngine:
         if (self.overlap & OVERLAP_CELLS) and R1 > 1024:
             # MultiRNNCell wavefront: cell 1 step t next to cell 0 step t+1 (fused-epilogue steps only: the
             # split-K path of the small-row steps shares one scratch buffer)
-            main, side = torch.cuda.current_stream(), self._side_stream()
-            h0_seq = a.h_all[1:]
-            for t in range(ell):
-                self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1, t, t + 1, main.cuda_stream)
-                ev = self._event(t)
-                ev.record(main)
-                side.wait_event(ev)
-                self._cell_fwd(b, h0_seq, R1 * H, H, 0, 1, self.len_l1, t, t + 1, side.cuda_stream)
-            main.wait_stream(side)
+            self._cells_interleaved(a, b, self.x, R1 * D, D, 0, self.len_l1)
         else:
             self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1)
             self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1)
         ops.state_pack(a.c_all[ell], a.h_all[ell], b.c_all[ell], b.h_all[ell], R1, H, out_bf16=self.l2_in)
         a2, b2 = self.l2
-        self._cell_fwd(a2, self.l2_in, B * S, S, 1, 0, self.len_l2)
-        self._cell_fwd(b2, a2.h_all[1:], B * H, H, 1, 1, self.len_l2)
+        if self.workspace2 is not None and B <= 1024:
+            self._cells_interleaved(a2, b2, self.l2_in, B * S, S, 1, self.len_l2, self.workspace2)
+        else:
+            self._cell_fwd(a2, self.l2_in, B * S, S, 1, 0, self.len_l2)
+            self._cell_fwd(b2, a2.h_all[1:], B * H, H, 1, 1, self.len_l2)
         ops.state_pack(a2.c_all[C], a2.h_all[C], b2.c_all[C], b2.h_all[C], B, H,
                        out_bf16=self.state_bf16, out_f32=self.state)
 

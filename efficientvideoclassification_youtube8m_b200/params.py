@@ -248,19 +248,33 @@ class HLstmParams:
         self._master_stale = False
 
     # ---- slim.learning.create_train_op: per-variable clip_by_norm + Adam (train.py:329-334)
-    def apply_gradients(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
-                        beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
-        """g <- g + penalty*l2_penalty*w for the two MoE matrices (gradient of
-        penalty * slim.l2_regularizer(l2_penalty)(w)), per-variable clip, TF Adam, bf16 refresh."""
-        wd = float(regularization_penalty) * self.cfg.l2_penalty
-        ops.fill_f32(self.normsq, 0.0)
-        ops.fill_f32(self.wsq, 0.0)
+    def begin_apply(self, lr: float, beta1: float = 0.9, beta2: float = 0.999) -> None:
+        """Advance the Adam step counter and compute lr_t once, for an update that is then applied in
+        several `apply_gradients(..., first=.., last=.., advance=False)` passes over slices of the variables."""
         ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
+
+    def apply_gradients(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
+                        beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                        first: int = 0, last: Optional[int] = None, advance: bool = True) -> None:
+        """g <- g + penalty*l2_penalty*w for the two MoE matrices (gradient of
+        penalty * slim.l2_regularizer(l2_penalty)(w)), per-variable clip, TF Adam, bf16 refresh.
+        Variables names[first:last] only (the clip is per variable, so a slice can be updated as soon as its
+        gradients are final); advance=False after `begin_apply`."""
+        wd = float(regularization_penalty) * self.cfg.l2_penalty
+        last = len(self.names) if last is None else last
+        ops.fill_f32(self.normsq[first:last], 0.0)
+        ops.fill_f32(self.wsq[first:last], 0.0)
+        if advance:
+            ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
         reg = (self.gates_w, self.experts_w)
         for i, n in enumerate(self.names):
+            if not first <= i < last:
+                continue
             w = self.w[n] if n in reg else None
             ops.sumsq(self.g[n], w, wd, self.normsq[i:i + 1], self.wsq[i:i + 1] if w is not None else None)
         for i, n in enumerate(self.names):
+            if not first <= i < last:
+                continue
             shadow = self.shadow.get(n)
             cols = self.shapes[n][1] if shadow is not None else 0
             ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],

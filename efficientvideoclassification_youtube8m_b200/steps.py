@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .engine import OVERLAP_STUDENT, HLstmEngine, overlap_mode
+from .engine import OVERLAP_OPTIMIZER, OVERLAP_STUDENT, HLstmEngine, overlap_mode
 from .params import HLstmParams, ModelConfig
 
 MAX_FRAMES = 300  # train.py:262
@@ -61,6 +61,7 @@ class _Base:
         self.global_step = 0
         self._pending = []
         self._gathers = []
+        self._opt_streams = {}
         # optimizer sharding over the data-parallel ranks (on by default when there is more than one)
         self.shard_optimizer = shard_optimizer if shard_optimizer is not None else (self._world() > 1)
 
@@ -113,6 +114,34 @@ class _Base:
             self._gathers += params.apply_gradients_sharded(self.lr, self.clip, self.penalty, dist.get_rank(), n)
         else:
             params.apply_gradients(self.lr, self.clip, self.penalty)
+
+    # ---- single-GPU schedule: the classifier's variables (2/3 of the parameters) have final gradients right
+    # after classifier_backward, so their clip+Adam pass (HBM-bound) runs on an optimizer stream next to the
+    # LSTM backward (tensor-bound) instead of after it.  With several ranks the optimizer is sharded and
+    # waits for the collectives instead.
+    def _early_apply_ok(self) -> bool:
+        return self._world() == 1 and bool(overlap_mode() & OVERLAP_OPTIMIZER) and self.device.type == "cuda"
+
+    def _opt_stream(self, params):
+        st = self._opt_streams.get(id(params))
+        if st is None:
+            st = self._opt_streams[id(params)] = (torch.cuda.Stream(device=self.device), torch.cuda.Event())
+        return st
+
+    def _apply_classifier_early(self, params):
+        """Call right after classifier_backward on the stream that ran it."""
+        cur = torch.cuda.current_stream()
+        opt, ev = self._opt_stream(params)
+        params.begin_apply(self.lr)
+        ev.record(cur)
+        opt.wait_event(ev)
+        with torch.cuda.stream(opt):
+            params.apply_gradients(self.lr, self.clip, self.penalty, first=8, advance=False)
+
+    def _apply_lstm_late(self, params):
+        """The other half of `_apply_classifier_early`, after lstm_backward."""
+        params.apply_gradients(self.lr, self.clip, self.penalty, first=0, last=8, advance=False)
+        torch.cuda.current_stream().wait_stream(self._opt_stream(params)[0])
 
     def _finish_gathers(self):
         for w in self._gathers:
@@ -170,7 +199,7 @@ class TeacherStudentTrainer(_Base):
                                if (overlap_mode() & OVERLAP_STUDENT) and self.device.type == "cuda" else None)
         self._teacher_ready = torch.cuda.Event() if self.student_stream is not None else None
 
-    def _forward_backward_two_streams(self, raw, num_frames, labels_u8):
+    def _forward_backward_two_streams(self, raw, num_frames, labels_u8, fuse_optimizer=False):
         B = self.B
         t, s = self.t_eng, self.s_eng
         main, side = torch.cuda.current_stream(), self.student_stream
@@ -189,14 +218,22 @@ class TeacherStudentTrainer(_Base):
             s.classifier_loss_fused(labels_u8, t.pred, 1.0 / B, 1.0, self.rows[1], self.rows[2])
             s.classifier_backward(None, dstate_preset=True, logits_done=True)
             self._reduce_grads(self.student, self.student.names[8:])
+            if fuse_optimizer:
+                self._apply_classifier_early(self.student)
         t.classifier_backward(None, logits_done=True)
         self._reduce_grads(self.teacher, self.teacher.names[8:])
+        if fuse_optimizer:
+            self._apply_classifier_early(self.teacher)
         t.lstm_backward()
         self._reduce_grads(self.teacher, self.teacher.names[:8])
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
+        if fuse_optimizer:
+            self._apply_lstm_late(self.teacher)
         with torch.cuda.stream(side):
             s.lstm_backward()
             self._reduce_grads(self.student, self.student.names[:8])
+            if fuse_optimizer:
+                self._apply_lstm_late(self.student)
             ops.reduce_rows(self.rows[1], 1.0 / B, self.losses[1:2])
             ops.reduce_rows(self.rows[2], 1.0, self.losses[2:3])
             ops.reduce_rows(self.rows[3], 1.0 / B, self.losses[3:4])
@@ -207,9 +244,9 @@ class TeacherStudentTrainer(_Base):
         if self.student_stream is not None:
             torch.cuda.current_stream().wait_stream(self.student_stream)
 
-    def _forward_backward(self, raw, num_frames, labels_u8):
+    def _forward_backward(self, raw, num_frames, labels_u8, fuse_optimizer=False):
         if self.student_stream is not None:
-            return self._forward_backward_two_streams(raw, num_frames, labels_u8)
+            return self._forward_backward_two_streams(raw, num_frames, labels_u8, fuse_optimizer)
         B = self.B
         t, s = self.t_eng, self.s_eng
         # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
@@ -253,8 +290,13 @@ class TeacherStudentTrainer(_Base):
         """One iteration = both train ops (global_step += 2).  Asynchronous; read
         results with :meth:`fetch`."""
         self._check(model_input_raw, num_frames, labels)
-        self._forward_backward(model_input_raw, num_frames, _as_u8(labels))
-        self.apply_gradients()
+        if self.student_stream is not None and self._early_apply_ok():
+            # optimizer passes are issued inside the schedule, each as soon as its gradients are final
+            self._forward_backward(model_input_raw, num_frames, _as_u8(labels), fuse_optimizer=True)
+            torch.cuda.current_stream().wait_stream(self.student_stream)
+        else:
+            self._forward_backward(model_input_raw, num_frames, _as_u8(labels))
+            self.apply_gradients()
         self.global_step += 2
 
     def fetch(self) -> Dict[str, float]:
@@ -296,10 +338,16 @@ class StudentFinetuneTrainer(_Base):
         s.classifier_loss_fused(_as_u8(labels), None, 1.0 / B, 0.0, self.rows[0], None)
         s.classifier_backward(None, logits_done=True)
         self._reduce_grads(self.student, self.student.names[8:])
+        early = self._early_apply_ok()
+        if early:
+            self._apply_classifier_early(self.student)
         s.lstm_backward()
         self._reduce_grads(self.student, self.student.names[:8])
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
-        self._apply(self.student)
+        if early:
+            self._apply_lstm_late(self.student)
+        else:
+            self._apply(self.student)
         self._finish_gathers()
         self.global_step += 1
 
