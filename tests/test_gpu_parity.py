@@ -286,3 +286,56 @@ def test_tfrecord_to_gpu_step(tmp_path):
     for k in fa:       # (the regulariser's sum of squares is accumulated with float atomics: order-dependent last bits)
         assert abs(fa[k] - fb[k]) <= 1e-6 * abs(fb[k]), k
     assert torch.equal(a.s_eng.pred, b.s_eng.pred) and torch.equal(a.t_eng.pred, b.t_eng.pred)
+
+
+@pytest.mark.parametrize("mode", [7, 31])
+def test_stream_schedules_equal_the_single_stream_step(mode, monkeypatch):
+    """EVC_OVERLAP only changes WHERE kernels run (streams joined by events), never what they compute: after
+    three training steps the multi-stream schedules hold the same predictions, losses and weights as the
+    single-stream one, up to the run-to-run noise the single-stream step has itself (two reductions use
+    float atomics: the bias column sums and the split-K d(state) of the classifier).  B=64 puts RNN_L1 of
+    the teacher (1280 rows) on the fused-epilogue path, so the step-by-step interleaving of the two cells
+    (evc_lstm_seq_fwd_steps) is exercised."""
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import StudentFinetuneTrainer, TeacherStudentTrainer
+    cfg = ModelConfig(**SMALL)
+    B = 64
+    x, nf, lab = O.synthetic_batch(B, seed=21, num_features=cfg.feature_size, vocab_size=cfg.vocab_size)
+    xd, nfd, labd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda(), torch.from_numpy(lab).cuda()
+
+    def run(overlap, cls):
+        monkeypatch.setenv("EVC_OVERLAP", str(overlap))
+        tr = cls(cfg, batch_size=B, device="cuda", base_learning_rate=1e-4)
+        tr.step(xd, nfd, labd)
+        first = tr.s_eng.pred.clone()          # forward of step 1: no atomics upstream, bit-identical
+        for _ in range(2):
+            tr.step(xd, nfd, labd)
+        out = tr.fetch()
+        torch.cuda.synchronize()
+        return tr, out, first
+
+    def models(tr):
+        return ([tr.teacher] if hasattr(tr, "teacher") else []) + [tr.student]
+
+    for cls in (TeacherStudentTrainer, StudentFinetuneTrainer):
+        a, fa, pa1 = run(0, cls)
+        a2, fa2, _ = run(0, cls)               # the single-stream step's own run-to-run noise
+        b, fb, pb1 = run(mode, cls)
+        if cls is TeacherStudentTrainer:
+            assert b.student_stream is not None and a.student_stream is None
+        assert torch.equal(pa1, pb1)
+        for k in fa:
+            noise = abs(fa[k] - fa2[k])
+            assert abs(fa[k] - fb[k]) <= 20 * noise + 2e-4 * abs(fa[k]) + 5e-6, (k, fa[k], fa2[k], fb[k])
+        noise = (a.s_eng.pred - a2.s_eng.pred).abs().max().item()
+        assert (a.s_eng.pred - b.s_eng.pred).abs().max().item() <= 20 * noise + 1e-5
+        for ma, ma2, mb in zip(models(a), models(a2), models(b)):
+            for n in ma.names:
+                d = (ma.w[n] - mb.w[n]).abs()
+                # Adam normalises the gradient: an element whose gradient is within the atomics' noise of zero
+                # may move by up to ~lr per step in either direction; everything else is equal to rounding
+                assert d.max().item() <= 3.5e-4, (n, d.max().item())
+                frac = (d > 1e-6).float().mean().item()
+                frac0 = ((ma.w[n] - ma2.w[n]).abs() > 1e-6).float().mean().item()
+                assert frac <= 20 * frac0 + 2e-3, (n, frac, frac0)
