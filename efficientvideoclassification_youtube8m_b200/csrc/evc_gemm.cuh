@@ -42,7 +42,7 @@ struct GemmArgs {
   int kb_total;        // number of 64-wide k blocks (A1 part + A2 part)
   int kb_a1;           // k blocks taken from tensor map A1; the remainder comes from A2
   int kb_per_split;
-  int debug;           // profiling experiments only (evc_debug_set): 1 = epilogue skips math+I/O, 2 = skips global I/O
+  int debug;           // profiling experiments only (evc_debug_set): 1024 = release the dependent grid at kernel start
   // ---- EPI_STORE
   void* C;
   long long ldc;
@@ -342,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                   if (col0 + j < args.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(args.bias + col0 + j));
               }
             }
-            if (col0 >= args.N || nrows <= 0 || (args.debug & 64)) continue;   // warp-uniform: nothing to store
+            if (col0 >= args.N || nrows <= 0) continue;   // warp-uniform: nothing to store
             // the box that used this buffer two iterations ago must have been read by the TMA engine
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
@@ -356,15 +356,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (args.debug & 512)   // experiment: every tile stores into the same 128x256 region (stays in L2)
-                tma_store_2d(&tmC, box, c0, q * 32);
-              else if (args.debug & 16) tma_store_2d(&tmC, box, col0, ks * args.split_rows + row0);
-              else if (!(args.debug & 32))   // streamed output must not evict the L2-resident operands
-                tma_store_2d_hint(&tmC, box, col0, ks * args.split_rows + row0, kL2EvictFirst);
+              // streamed output must not evict the L2-resident operands
+              tma_store_2d_hint(&tmC, box, col0, ks * args.split_rows + row0, kL2EvictFirst);
               tma_store_commit();
             }
             buf ^= 1;
-            if (args.debug >> 16) __nanosleep(args.debug >> 16);   // experiment: pace the output stores
           }
           if (lane == 0) tma_store_wait_read<0>();              // staging is free again for the next tile
           __syncwarp();
@@ -376,7 +372,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           tmem_ld_wait();
           const int col0 = n_blk * BN + c0;
           if (col0 >= args.N || nrows <= 0) continue;   // warp-uniform
-          if (args.debug & 64) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -405,7 +400,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             if (!args.atomic_add && vec) {
               stage_put_f32(st_f, lane, v);
               __syncwarp();
-              if (!(args.debug & 32)) flush_f32(st_f, cp, args.ldc, nrows, lane);
+              flush_f32(st_f, cp, args.ldc, nrows, lane);
               __syncwarp();
             } else if (args.atomic_add) {
               stage_put_f32(st_f, lane, v);

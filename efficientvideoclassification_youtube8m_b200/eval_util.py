@@ -88,10 +88,27 @@ def calculate_gap(predictions, actuals, top_k=20):
     return gap_calculator.peek_ap_at_n()
 
 
-class EvaluationMetrics(object):
-    """eval_util.py:126-213."""
+def batch_stats(predictions, labels, loss, top_k):
+    """What one batch contributes to EvaluationMetrics, as small host arrays: the per-video top-k triplets
+    (selected on the GPU), the positives per class, and the hit@1 / PERR / loss sums."""
+    p, a = _dev(predictions, labels)
+    batch_size = int(a.shape[0])
+    idx, val, lab = top_k_device(p, a, top_k)
+    mean_loss = float(np.mean(loss.cpu().numpy() if torch.is_tensor(loss) else loss))
+    return {"n": batch_size, "idx": idx, "val": val, "lab": lab,
+            "num_positives": a.sum(dim=0).cpu().numpy().astype(np.float64),
+            "hit_sum": calculate_hit_at_one(p, a) * batch_size,
+            "perr_sum": calculate_precision_at_equal_recall_rate(p, a) * batch_size,
+            "loss_sum": mean_loss * batch_size}
 
-    def __init__(self, num_class, top_k):
+
+class EvaluationMetrics(object):
+    """eval_util.py:126-213.  With `distributed=True` under an initialised torch.distributed group every
+    rank evaluates its own shard of the videos and `accumulate` all-gathers the per-batch statistics
+    (k triplets per video + label counts), so that all ranks hold the metrics of the global
+    batch -- the same numbers one process would compute on the concatenation of the shards in rank order."""
+
+    def __init__(self, num_class, top_k, distributed=False, group=None):
         self.sum_hit_at_one = 0.0
         self.sum_perr = 0.0
         self.sum_loss = 0.0
@@ -99,20 +116,46 @@ class EvaluationMetrics(object):
         self.global_ap_calculator = AveragePrecisionCalculator()
         self.top_k = top_k
         self.num_examples = 0
+        self.num_class = num_class
+        self.distributed = distributed
+        self.group = group
 
     def accumulate(self, predictions, labels, loss):
-        batch_size = labels.shape[0]
-        mean_hit_at_one = calculate_hit_at_one(predictions, labels)
-        mean_perr = calculate_precision_at_equal_recall_rate(predictions, labels)
-        mean_loss = float(np.mean(loss.cpu().numpy() if torch.is_tensor(loss) else loss))
-        sparse_predictions, sparse_labels, num_positives = top_k_by_class(predictions, labels, self.top_k)
-        self.map_calculator.accumulate(sparse_predictions, sparse_labels, num_positives)
-        self.global_ap_calculator.accumulate(flatten(sparse_predictions), flatten(sparse_labels), sum(num_positives))
-        self.num_examples += batch_size
-        self.sum_hit_at_one += mean_hit_at_one * batch_size
-        self.sum_perr += mean_perr * batch_size
-        self.sum_loss += mean_loss * batch_size
-        return {"hit_at_one": mean_hit_at_one, "perr": mean_perr, "loss": mean_loss}
+        return self.accumulate_stats(batch_stats(predictions, labels, loss, self.top_k))
+
+    def accumulate_stats(self, stats):
+        """Fold the statistics of one batch (`batch_stats`) of this rank -- and, when distributed, of the same
+        batch index of every other rank -- into the accumulators."""
+        parts = [stats]
+        if self.distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                parts = [None] * dist.get_world_size(self.group)
+                dist.all_gather_object(parts, stats, group=self.group)
+        n = hit = perr = loss = 0.0
+        for st in parts:
+            if st["n"] == 0:
+                continue
+            sparse_predictions = [[] for _ in range(self.num_class)]
+            sparse_labels = [[] for _ in range(self.num_class)]
+            for c, v, t in zip(st["idx"].reshape(-1), st["val"].reshape(-1), st["lab"].reshape(-1)):
+                sparse_predictions[c].append(float(v))
+                sparse_labels[c].append(float(t))
+            num_positives = st["num_positives"].tolist()
+            self.map_calculator.accumulate(sparse_predictions, sparse_labels, num_positives)
+            self.global_ap_calculator.accumulate(flatten(sparse_predictions), flatten(sparse_labels),
+                                                 sum(num_positives))
+            n += st["n"]
+            hit += st["hit_sum"]
+            perr += st["perr_sum"]
+            loss += st["loss_sum"]
+        self.num_examples += int(n)
+        self.sum_hit_at_one += hit
+        self.sum_perr += perr
+        self.sum_loss += loss
+        if n == 0:
+            return {"hit_at_one": 0.0, "perr": 0.0, "loss": 0.0}
+        return {"hit_at_one": hit / n, "perr": perr / n, "loss": loss / n}
 
     def get(self):
         if self.num_examples <= 0:

@@ -35,7 +35,9 @@ const char* evc_last_error(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 long long evc_launch_count(void);
 
-/* profiling experiments only: bit flags that disable parts of the GEMM epilogues (scripts/exp_*.py) */
+/* profiling experiments only (bit flags): 128 = plain GEMMs store through the LSU path instead of TMA bulk
+ * stores, 256 = no programmatic dependent launch for the GEMM kernels, 1024 = release the dependent grid at
+ * kernel start instead of at the last tile.  Also settable with the EVC_DEBUG environment variable. */
 int evc_debug_set(int flags);
 
 /* ---- input: tf.nn.l2_normalize (train.py:256) + uniform gather (train.py:265-272) or

@@ -45,3 +45,88 @@ def test_gradient_average_world2():
         out = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _stats_from_oracle(O, p, a, loss, k):
+    """batch_stats() computed on the host by the oracle (the product computes the top-k on the GPU)."""
+    import numpy as np
+    n = p.shape[0]
+    if n == 0:
+        z = np.zeros((0, k))
+        return {"n": 0, "idx": z.astype(np.int32), "val": z.astype(np.float32), "lab": z.astype(np.uint8),
+                "num_positives": np.zeros(p.shape[1]), "hit_sum": 0.0, "perr_sum": 0.0, "loss_sum": 0.0}
+    idx, val = O.top_k(p, k)
+    return {"n": n, "idx": idx, "val": val.astype(np.float32), "lab": np.take_along_axis(a, idx, axis=1),
+            "num_positives": a.sum(0).astype(np.float64), "hit_sum": O.hit_at_one(p, a) * n,
+            "perr_sum": O.perr(p, a) * n, "loss_sum": float(loss) * n}
+
+
+def _eval_batches(world):
+    """Two evaluation batches per rank, the last one ragged (rank 0: 5 videos, rank 1: none)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    V = 40
+    out = []
+    for b, sizes in enumerate([(6, 6), (5, 0)]):
+        per_rank = []
+        for r in range(world):
+            n = sizes[r]
+            p = rng.random((n, V)).astype(np.float32)        # distinct values: no tie order involved
+            a = (rng.random((n, V)) < 0.1).astype(np.uint8)
+            per_rank.append((p, a, 1.0 + b + 0.1 * r))
+        out.append(per_rank)
+    return V, out
+
+
+def _metrics_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.eval_util import EvaluationMetrics
+    V, batches = _eval_batches(world)
+    m = EvaluationMetrics(V, 5, distributed=True)
+    per_batch = []
+    for per_rank in batches:
+        p, a, loss = per_rank[rank]
+        per_batch.append(m.accumulate_stats(_stats_from_oracle(O, p, a, loss, 5)))
+    res = m.get()
+    out[rank] = (per_batch, res["avg_hit_at_one"], res["avg_perr"], res["avg_loss"], res["gap"],
+                 [float(x) for x in res["aps"]], m.num_examples)
+    dist.destroy_process_group()
+
+
+def test_distributed_evaluation_metrics_world2():
+    """evaluation shards the videos over the ranks and all-gathers k triplets per video; every
+    rank ends with the metrics one process computes on the concatenated batches."""
+    import numpy as np
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200.eval_util import EvaluationMetrics
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_metrics_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        got = dict(out)
+    assert got[0] == got[1]                                   # all ranks hold the same global metrics
+    V, batches = _eval_batches(world)
+    single = EvaluationMetrics(V, 5)
+    all_p, all_a, want_batch = [], [], []
+    for per_rank in batches:
+        p = np.concatenate([x[0] for x in per_rank])
+        a = np.concatenate([x[1] for x in per_rank])
+        loss = sum(x[2] * x[0].shape[0] for x in per_rank) / p.shape[0]
+        want_batch.append(single.accumulate_stats(_stats_from_oracle(O, p, a, loss, 5)))
+        all_p.append(p)
+        all_a.append(a)
+    want = single.get()
+    assert len(np.unique(np.concatenate(all_p))) == 17 * V
+    per_batch, hit, perr, loss, gap, aps, n = got[0]
+    assert n == 17
+    for g, w in zip(per_batch, want_batch):
+        for k in w:
+            assert abs(g[k] - w[k]) < 1e-12, (k, g[k], w[k])
+    assert abs(hit - want["avg_hit_at_one"]) < 1e-12 and abs(perr - want["avg_perr"]) < 1e-12
+    assert abs(loss - want["avg_loss"]) < 1e-12
+    assert abs(gap - want["gap"]) < 1e-12 and np.allclose(aps, want["aps"], atol=1e-12)
+    # and the global GAP equals the oracle's AP over the pooled top-k triplets of all 17 videos
+    # (distinct prediction values: no tie order involved)
+    assert abs(gap - O.gap(np.concatenate(all_p), np.concatenate(all_a), 5)) < 1e-12
