@@ -10,7 +10,10 @@ not installable here (no network), and the reference ships no tests or golden
 vectors for this path.  This file restates the published TF r1.3/r1.4 semantics
 of the ops the reference calls; the only anchors are the
 reference's call sites and the README training log (CE at init = 1914.1,
-``README.md:116``), which ``tests/test_oracle.py`` reproduces.  The top-k / GAP
+``README.md:116``), which ``tests/test_oracle.py`` reproduces, plus cross-checks of
+every restated op against PyTorch's independent implementations of the same
+algorithms (``tests/test_oracle_crosscheck.py``: LSTMCell / packed LSTM, Categorical
+KL, Adam, clip_grad_norm_, normalize, BCE).  The top-k / GAP
 part of the path *is* pinned: ``tests/golden/make_golden_eval.py`` imports the
 reference's own ``eval_util.py`` and records its outputs.
 
