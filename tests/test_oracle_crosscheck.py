@@ -149,3 +149,54 @@ def test_moe_equals_a_per_class_loop():
             gate = np.exp(gl - gl.max()); gate /= gate.sum()
             ex = 1.0 / (1.0 + np.exp(-E[b, c * M:(c + 1) * M]))
             assert abs(got[b, c].item() - float((gate[:M] * ex).sum())) < 1e-13
+
+
+def _torch_lstm2(cells, in_dim, H):
+    lstm = torch.nn.LSTM(in_dim, H, num_layers=2, batch_first=True, dtype=D64)
+    with torch.no_grad():
+        for layer, ((kernel, bias), d) in enumerate(zip(cells, (in_dim, H))):
+            w_ih, w_hh, b, _ = _tf_to_torch_lstm(kernel, bias, d)
+            getattr(lstm, f"weight_ih_l{layer}").copy_(w_ih)
+            getattr(lstm, f"weight_hh_l{layer}").copy_(w_hh)
+            getattr(lstm, f"bias_ih_l{layer}").copy_(b)
+            getattr(lstm, f"bias_hh_l{layer}").zero_()
+    return lstm
+
+
+def _final_state(lstm, x, length, H):
+    """[c0|h0|c1|h1] of ONE sequence after `length` steps from the zero state (zero if length == 0)."""
+    if length == 0:
+        return torch.zeros(4 * H, dtype=D64)
+    with torch.no_grad():
+        _, (h_n, c_n) = lstm(x[None, :length])
+    return torch.cat([c_n[0, 0], h_n[0, 0], c_n[1, 0], h_n[1, 0]])
+
+
+def test_hierarchical_state_equals_a_literal_per_video_per_chunk_loop():
+    """frame_level_models.py:237-257 executed literally -- video by video, chunk by chunk: tf.split into
+    num_inputs_to_lstm chunks, each chunk through RNN_L1 from the zero state for
+    min(len, max(0, n - len*i)) steps, the chunk states stacked and run through RNN_L2 for ceil(n/len)
+    steps -- with torch.nn.LSTM as the cell engine.  The oracle batches all chunks into one call."""
+    g = torch.Generator().manual_seed(11)
+    D, H, C, ell = 10, 8, 5, 4                       # 20 frames = 5 chunks x 4
+    T = C * ell
+    mk = lambda r, c: torch.randn(r, c, generator=g, dtype=D64) * 0.4
+    params = {}
+    for level, in_dim in (("RNN_L1", D), ("RNN_L2", 4 * H)):
+        for cell, d in ((0, in_dim), (1, H)):
+            base = f"m/{level}/rnn/multi_rnn_cell/cell_{cell}/basic_lstm_cell"
+            params[base + "/kernel"] = mk(d + H, 4 * H)
+            params[base + "/bias"] = mk(1, 4 * H)[0]
+    num_frames = np.array([1, 3, 4, 5, 8, 9, 12, 16, 17, 19, 20], dtype=np.int32)
+    x = torch.randn(len(num_frames), T, D, generator=g, dtype=D64)
+    for b, n in enumerate(num_frames):
+        x[b, n:] = 0.0                               # readers.py:173 zero padding
+    got = O.hlstm_state(x, num_frames, params, "m", C)
+    l1 = _torch_lstm2(O._cells(params, "m", "RNN_L1"), D, H)
+    l2 = _torch_lstm2(O._cells(params, "m", "RNN_L2"), 4 * H, H)
+    for b, n in enumerate(num_frames):
+        chunks = [_final_state(l1, x[b, i * ell:(i + 1) * ell], int(min(ell, max(0, n - ell * i))), H)
+                  for i in range(C)]
+        len2 = int(np.ceil(np.float32(n) / np.float32(ell)))
+        want = _final_state(l2, torch.stack(chunks), len2, H)
+        assert torch.allclose(got[b], want, atol=1e-13), (b, n)
