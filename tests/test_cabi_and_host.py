@@ -121,3 +121,38 @@ def test_bench_gpu_arm_does_not_import_the_oracle():
         if f.endswith(".py"):
             text = open(os.path.join(pkg, f)).read()
             assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    """The C ABI validates its arguments on the host and reports through the int return code +
+    evc_last_error() (no exceptions, no launch): checked here without a GPU."""
+    from efficientvideoclassification_youtube8m_b200 import _lib
+    lib = _lib.lib
+    # evc_lstm_seq_fwd_steps: empty problem, bad step range, H not a multiple of 64
+    args = dict(x=None, stride=0, Kx=128, W=None, bias=None, rows=128, H=128, T=4, t0=0, t1=4)
+
+    def call(**kw):
+        a = dict(args, **kw)
+        return lib.evc_lstm_seq_fwd_steps(a["x"], a["stride"], a["Kx"], a["W"], a["bias"], a["rows"], a["H"], a["T"],
+                                          a["t0"], a["t1"], None, None, None, None, None, 0, None)
+    assert call(rows=0) == -1 and b"empty" in lib.evc_last_error()
+    for t0, t1 in ((-1, 2), (3, 2), (0, 5), (2, 2)):
+        assert call(t0=t0, t1=t1) == -1 and b"step range" in lib.evc_last_error()
+    assert call(H=100) == -1 and b"multiples of 64" in lib.evc_last_error()
+    with pytest.raises(_lib.EvcError, match="step range"):
+        _lib.check(call(t0=3, t1=1), "evc_lstm_seq_fwd_steps")
+    # evc_frames_pack: frames must split evenly into chunks (tf.split), features a multiple of 4
+    assert lib.evc_frames_pack(None, 2, 300, 128, None, 0, 30, 7, 1, None, None, None) == -1
+    assert b"split evenly" in lib.evc_last_error()
+    assert lib.evc_frames_pack(None, 2, 300, 126, None, 0, 30, 5, 1, None, None, None) == -1
+    # evc_topk: k must be positive and <= num_classes (eval_util.py:103-104)
+    assert lib.evc_topk(None, 4, 100, 0, None, None, None, None, None) == -1
+    assert lib.evc_topk(None, 4, 100, 101, None, None, None, None, None) == -1
+
+
+def test_overlap_mode_default_and_env(monkeypatch):
+    from efficientvideoclassification_youtube8m_b200 import engine
+    monkeypatch.delenv("EVC_OVERLAP", raising=False)
+    assert engine.overlap_mode() == (engine.OVERLAP_STUDENT | engine.OVERLAP_CELLS | engine.OVERLAP_WGRAD)
+    monkeypatch.setenv("EVC_OVERLAP", "0")
+    assert engine.overlap_mode() == 0
