@@ -278,9 +278,9 @@ def run_ours(args):
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
-            # capture committed as profiles/r01_fwd_kernel_ncu_full_summary.txt (65.2 MB + 36.3 MB); the
-            # algorithmic bytes are 61 MB read (x_t, h, W, c) + 73.5 MB written (c, h, gates), the L2 absorbs part
-            "traffic": None if finetune else 101.5e6, "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst bf16",
+            # capture summarised in profiles/r01_ncu_kernels_summary.txt (64.5 MB + 36.3 MB); the algorithmic
+            # bytes are 61 MB read (x_t, h, W, c) + 73.5 MB written (c, h, gates), the L2 absorbs part
+            "traffic": None if finetune else 100.8e6, "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst bf16",
             "launches_timed": ell, "avg_launch_ms": ms_seq / ell}
 
     # ---------------- student inference (BASELINE config #2), device resident
