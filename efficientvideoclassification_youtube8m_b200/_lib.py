@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libevc.so")
+# EVC_LIB_PATH: load another build of the same sources (scripts/exp_epilogue_ablation.py builds one with
+# -DEVC_ABLATE); the product always uses the in-tree library
+LIB_PATH = os.environ.get("EVC_LIB_PATH") or os.path.join(_HERE, "libevc.so")
 
 P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
