@@ -10,11 +10,43 @@ float32 batches.
 """
 from __future__ import annotations
 
+import ctypes
+import os
+import queue
 import struct
-from typing import Dict, Iterable, Iterator, List, Sequence, Tuple
+import threading
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+
+# ------------------------------------------------------------------ native decoder (include/evc_reader.h)
+READER_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libevc_reader.so")
+_reader_lib = None
+
+
+def reader_lib():
+    """ctypes binding of libevc_reader.so (csrc/evc_reader.cpp: multi-threaded TFRecord + SequenceExample
+    decoder writing straight into the caller's pinned batch buffers)."""
+    global _reader_lib
+    if _reader_lib is None:
+        if not os.path.exists(READER_LIB_PATH):
+            raise ImportError(f"{READER_LIB_PATH} not found: build it with "
+                              "`python -c 'import __graft_entry__ as g; g.build()'` from the repo root.")
+        lib = ctypes.CDLL(READER_LIB_PATH)
+        P, I, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+        lib.evc_reader_version.argtypes, lib.evc_reader_version.restype = [], I
+        lib.evc_reader_last_error.argtypes, lib.evc_reader_last_error.restype = [], ctypes.c_char_p
+        lib.evc_reader_open.argtypes = [ctypes.POINTER(ctypes.c_char_p), I, ctypes.POINTER(ctypes.c_char_p),
+                                        ctypes.POINTER(I), I, I, I, I, I]
+        lib.evc_reader_open.restype = P
+        lib.evc_reader_next.argtypes, lib.evc_reader_next.restype = [P, I, P, P, P, P, I], I
+        lib.evc_reader_position.argtypes, lib.evc_reader_position.restype = [P], L
+        lib.evc_reader_rewind.argtypes, lib.evc_reader_rewind.restype = [P], I
+        lib.evc_reader_close.argtypes, lib.evc_reader_close.restype = [P], None
+        lib.evc_crc32c_masked.argtypes, lib.evc_crc32c_masked.restype = [ctypes.c_char_p, L], ctypes.c_uint
+        _reader_lib = lib
+    return _reader_lib
 
 
 class BaseReader(object):
@@ -158,10 +190,16 @@ def make_sequence_example(video_id: str, labels: Sequence[int], features: Dict[s
     return _ld(1, ctx) + _ld(2, fl)
 
 
-def write_tfrecord(path: str, records: Iterable[bytes]) -> None:
+def write_tfrecord(path: str, records: Iterable[bytes], with_crc: bool = False) -> None:
+    """TFRecord framing; with_crc=True stores the masked CRC32C of the length and of the payload like
+    TensorFlow's writer (computed by the native library), otherwise zeros."""
+    crc = reader_lib().evc_crc32c_masked if with_crc else None
     with open(path, "wb") as f:
         for r in records:
-            f.write(struct.pack("<Q", len(r)) + b"\0\0\0\0" + r + b"\0\0\0\0")
+            head = struct.pack("<Q", len(r))
+            c1 = struct.pack("<I", crc(head, 8)) if crc else b"\0\0\0\0"
+            c2 = struct.pack("<I", crc(r, len(r))) if crc else b"\0\0\0\0"
+            f.write(head + c1 + r + c2)
 
 
 # ------------------------------------------------------------------ the reader
@@ -205,10 +243,64 @@ class YT8MFrameFeatureReader(BaseReader):
                     col += size
                 yield vid, mat, labels, min(max(num_frames, 0), self.max_frames)
 
-    def batches(self, filenames, batch_size, drop_remainder=False, pin_memory=None):
-        """Collates prepare_reader into (ids, uint8 [B,max_frames,D], bool [B,num_classes], int32 [B])
-        torch tensors (pinned when CUDA is available) ready for `Trainer.step`."""
+    def batches(self, filenames, batch_size, drop_remainder=False, pin_memory=None, native=True,
+                num_threads=0, verify_crc=False, prefetch=0):
+        """(ids, uint8 [B,max_frames,D], bool [B,num_classes], int32 [B]) torch tensors (pinned when CUDA is
+        available) ready for `Trainer.step`.
+
+        native=True: the shards are decoded by libevc_reader (num_threads worker threads, 0 = one per hardware
+        thread) straight into the pinned batch tensors; prefetch=N decodes up to N batches ahead on a
+        background thread (the C call releases the GIL), so decoding overlaps the GPU step.
+        native=False: the pure-Python decoder above (reference implementation of the wire format, pinned
+        against the protobuf library in tests/test_readers.py)."""
         pin = torch.cuda.is_available() if pin_memory is None else pin_memory
+        if native:
+            # prefetch > 0: a ring of prefetch + 2 pinned buffer sets is reused (one being filled, `prefetch`
+            # queued, one in the consumer's hands) -- a batch is valid until the consumer asks for the one after
+            # the next; prefetch = 0 allocates fresh tensors for every batch.
+            it = self._native_batches(list(filenames), batch_size, drop_remainder, pin, num_threads, verify_crc,
+                                      ring=prefetch + 2 if prefetch > 0 else 0)
+            return _prefetched(it, prefetch) if prefetch > 0 else it
+        return self._python_batches(filenames, batch_size, drop_remainder, pin)
+
+    def _native_batches(self, filenames, batch_size, drop_remainder, pin, num_threads, verify_crc, ring=0):
+        lib = reader_lib()
+        D, V, T = sum(self.feature_sizes), self.num_classes, self.max_frames
+        paths = (ctypes.c_char_p * len(filenames))(*[os.fsencode(p) for p in filenames])
+        names = (ctypes.c_char_p * len(self.feature_names))(*[n.encode() for n in self.feature_names])
+        sizes = (ctypes.c_int * len(self.feature_sizes))(*self.feature_sizes)
+        handle = lib.evc_reader_open(paths, len(filenames), names, sizes, len(self.feature_names), V, T,
+                                     int(num_threads), int(bool(verify_crc)))
+        if not handle:
+            raise IOError(lib.evc_reader_last_error().decode())
+        id_stride = 64
+
+        def alloc():
+            return (torch.empty(batch_size, T, D, dtype=torch.uint8, pin_memory=pin),
+                    torch.empty(batch_size, V, dtype=torch.uint8, pin_memory=pin),
+                    torch.empty(batch_size, dtype=torch.int32, pin_memory=pin))
+
+        buffers = [alloc() for _ in range(ring)]
+        turn = 0
+        try:
+            while True:
+                x, y, n = buffers[turn % ring] if ring else alloc()
+                turn += 1
+                ids = ctypes.create_string_buffer(batch_size * id_stride)
+                got = lib.evc_reader_next(handle, batch_size, x.data_ptr(), y.data_ptr(), n.data_ptr(), ids, id_stride)
+                if got < 0:
+                    raise ValueError(lib.evc_reader_last_error().decode())
+                if got == 0 or (got < batch_size and drop_remainder):
+                    return
+                raw = ids.raw
+                vid = [raw[i * id_stride:(i + 1) * id_stride].split(b"\0", 1)[0].decode("utf-8") for i in range(got)]
+                yield vid, x[:got], y[:got].view(torch.bool), n[:got]
+                if got < batch_size:
+                    return
+        finally:
+            lib.evc_reader_close(handle)
+
+    def _python_batches(self, filenames, batch_size, drop_remainder, pin):
         ids, feats, labs, nfs = [], [], [], []
 
         def emit():
@@ -226,3 +318,26 @@ class YT8MFrameFeatureReader(BaseReader):
                 ids, feats, labs, nfs = [], [], [], []
         if ids and not drop_remainder:
             yield emit()
+
+
+def _prefetched(it, depth):
+    """Runs the iterator `it` on a background thread, `depth` items ahead."""
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    done = object()
+
+    def worker():
+        try:
+            for item in it:
+                q.put(item)
+            q.put(done)
+        except BaseException as e:      # re-raised in the consumer
+            q.put(e)
+
+    threading.Thread(target=worker, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is done:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item

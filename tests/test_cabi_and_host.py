@@ -156,3 +156,23 @@ def test_overlap_mode_default_and_env(monkeypatch):
     assert engine.overlap_mode() == (engine.OVERLAP_STUDENT | engine.OVERLAP_CELLS | engine.OVERLAP_WGRAD)
     monkeypatch.setenv("EVC_OVERLAP", "0")
     assert engine.overlap_mode() == 0
+
+
+def test_reader_library_exports_every_declared_symbol():
+    """include/evc_reader.h <-> libevc_reader.so (the native host-side input path; built by build() with g++)."""
+    import __graft_entry__ as g
+    g.build()
+    src = open(os.path.join(ROOT, "include", "evc_reader.h")).read()
+    syms = sorted(set(re.findall(r"\b(evc_[a-z0-9_]+)\s*\(", src)))
+    assert len(syms) == 8, syms
+    lib = ctypes.CDLL(os.path.join(ROOT, "efficientvideoclassification_youtube8m_b200", "libevc_reader.so"))
+    for s in syms:
+        assert hasattr(lib, s), f"libevc_reader.so does not export {s}"
+    lib.evc_reader_version.restype = ctypes.c_int
+    assert lib.evc_reader_version() >= 1
+    # argument errors come back as NULL / negative codes with a message, never as a crash
+    lib.evc_reader_open.restype = ctypes.c_void_p
+    lib.evc_reader_last_error.restype = ctypes.c_char_p
+    assert lib.evc_reader_open(None, 0, None, None, 0, 10, 300, 1, 0) is None
+    assert b"feature_names is empty" in lib.evc_reader_last_error()
+    assert lib.evc_reader_next(None, 4, None, None, None, None, 0) == -1

@@ -82,7 +82,8 @@ def test_wire_codec_against_protobuf_library():
     assert ex2 == ex
 
 
-def test_reader_batches_match_reference_semantics(tmp_path):
+@pytest.mark.parametrize("native", [False, True])
+def test_reader_batches_match_reference_semantics(tmp_path, native):
     from efficientvideoclassification_youtube8m_b200 import readers
     rng = np.random.default_rng(1)
     sizes = [("rgb", 32), ("audio", 8)]
@@ -96,7 +97,7 @@ def test_reader_batches_match_reference_semantics(tmp_path):
     path = str(tmp_path / "train0.tfrecord")
     readers.write_tfrecord(path, recs)
     rd = readers.YT8MFrameFeatureReader(num_classes=50, feature_sizes=[32, 8], feature_names=["rgb", "audio"])
-    out = list(rd.batches([path], batch_size=3, pin_memory=False))
+    out = list(rd.batches([path], batch_size=3, pin_memory=False, native=native))
     assert [len(b[0]) for b in out] == [3, 1]
     ids = sum((b[0] for b in out), [])
     x = torch.cat([b[1] for b in out]); y = torch.cat([b[2] for b in out]); nf = torch.cat([b[3] for b in out])
@@ -113,3 +114,95 @@ def test_reader_batches_match_reference_semantics(tmp_path):
         assert deq[k:].sum() == 0 and abs(deq[:k].mean()) < 2.0
     with pytest.raises(AssertionError):
         readers.YT8MFrameFeatureReader(feature_sizes=[1024, 128], feature_names=["rgb"])
+
+
+def _protobuf_record(SequenceExample, vid, labels, feats, packed_labels=True):
+    ex = SequenceExample()
+    ex.context.feature["id"].bytes_list.value.append(vid.encode())
+    ex.context.feature["labels"].int64_list.value.extend(labels)
+    for name, mat in feats.items():
+        flist = ex.feature_lists.feature_list[name]          # present (and empty) also for a video without frames
+        for row in mat:
+            flist.feature.add().bytes_list.value.append(row.tobytes())
+    return ex.SerializeToString()
+
+
+def test_native_reader_equals_python_reader_on_library_serialised_shards(tmp_path):
+    """libevc_reader (csrc/evc_reader.cpp) against the pure-Python decoder on records serialised by the
+    protobuf LIBRARY (map entries, packed int64 labels, negative and out-of-range labels, an extra feature
+    list the reader does not ask for), spread over three shards incl. an empty one, with TensorFlow-style
+    CRCs verified; every thread count and batch size gives the same batches."""
+    from efficientvideoclassification_youtube8m_b200 import readers
+    SequenceExample = _tf_example_messages()
+    rng = np.random.default_rng(3)
+    sizes = [("rgb", 24), ("audio", 8), ("extra", 5)]
+    shards = [[], [], []]
+    for i in range(23):
+        n = int(rng.integers(0, 330)) if i % 5 else (0 if i == 0 else 300)
+        labels = rng.choice(60, size=int(rng.integers(0, 5)), replace=False).tolist() + ([-1, 50, 4096] if i % 4 == 0 else [])
+        shards[0 if i < 9 else 2].append(_protobuf_record(SequenceExample, f"video-{i}", labels, _video(rng, n, sizes)))
+    paths = []
+    for k, recs in enumerate(shards):
+        paths.append(str(tmp_path / f"train{k}.tfrecord"))
+        readers.write_tfrecord(paths[-1], recs, with_crc=True)
+    rd = readers.YT8MFrameFeatureReader(num_classes=50, feature_sizes=[24, 8], feature_names=["rgb", "audio"])
+    want = list(rd.batches(paths, 4, pin_memory=False, native=False))
+    assert sum(len(b[0]) for b in want) == 23
+    for threads, prefetch in ((1, 0), (3, 0), (8, 2)):
+        got = list((ids, x.clone(), y.clone(), n.clone()) for ids, x, y, n in
+                   rd.batches(paths, 4, pin_memory=False, native=True, num_threads=threads, verify_crc=True,
+                              prefetch=prefetch))
+        assert len(got) == len(want)
+        for (ia, xa, ya, na), (ib, xb, yb, nb) in zip(want, got):
+            assert ia == ib and torch.equal(xa, xb) and torch.equal(ya, yb) and torch.equal(na, nb)
+            assert yb.dtype == torch.bool and nb.dtype == torch.int32
+    # drop_remainder and a batch size that does not divide the stream
+    assert [len(b[0]) for b in rd.batches(paths, 5, pin_memory=False, drop_remainder=True)] == [5, 5, 5, 5]
+
+
+def test_native_reader_errors(tmp_path):
+    from efficientvideoclassification_youtube8m_b200 import readers
+    rng = np.random.default_rng(4)
+    rd = readers.YT8MFrameFeatureReader(num_classes=50, feature_sizes=[24, 8], feature_names=["rgb", "audio"])
+    good = readers.make_sequence_example("ok", [1], _video(rng, 3, [("rgb", 24), ("audio", 8)]))
+    # corrupted payload under CRC verification (TFRecordReader raises DataLossError)
+    p = str(tmp_path / "a.tfrecord")
+    readers.write_tfrecord(p, [good], with_crc=True)
+    raw = bytearray(open(p, "rb").read())
+    raw[40] ^= 0xFF
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="CRC32C"):
+        list(rd.batches([p], 2, pin_memory=False, verify_crc=True))
+    # feature lists of different lengths (readers.py:218-219 asserts equal num_frames)
+    bad = readers.make_sequence_example("bad", [1], {"rgb": _video(rng, 3, [("rgb", 24)])["rgb"],
+                                                      "audio": _video(rng, 2, [("audio", 8)])["audio"]})
+    p2 = str(tmp_path / "b.tfrecord")
+    readers.write_tfrecord(p2, [good, bad])
+    with pytest.raises(ValueError, match="frames"):
+        list(rd.batches([p2], 2, pin_memory=False))
+    with pytest.raises(ValueError):
+        list(rd.batches([p2], 2, pin_memory=False, native=False))
+    # a missing feature list, a truncated file, a missing file
+    p3 = str(tmp_path / "c.tfrecord")
+    readers.write_tfrecord(p3, [readers.make_sequence_example("x", [1], _video(rng, 3, [("rgb", 24)]))])
+    with pytest.raises(ValueError, match="audio"):
+        list(rd.batches([p3], 2, pin_memory=False))
+    p4 = str(tmp_path / "d.tfrecord")
+    open(p4, "wb").write(open(p2, "rb").read()[:-9])
+    with pytest.raises(ValueError, match="truncated"):
+        list(rd.batches([p4], 2, pin_memory=False))
+    with pytest.raises(ValueError, match="cannot open"):
+        list(rd.batches([str(tmp_path / "nope.tfrecord")], 2, pin_memory=False))
+
+
+def test_masked_crc32c_known_answers():
+    """CRC-32C check values (RFC 3720 B.4) through TensorFlow's mask: ((crc >> 15 | crc << 17) + 0xa282ead8)."""
+    from efficientvideoclassification_youtube8m_b200 import readers
+    lib = readers.reader_lib()
+
+    def mask(c):
+        return (((c >> 15) | (c << 17)) + 0xa282ead8) & 0xFFFFFFFF
+    assert lib.evc_crc32c_masked(b"123456789", 9) == mask(0xE3069283)
+    assert lib.evc_crc32c_masked(bytes(32), 32) == mask(0x8A9136AA)
+    assert lib.evc_crc32c_masked(bytes([0xFF] * 32), 32) == mask(0x62A8AB43)
+    assert lib.evc_crc32c_masked(bytes(range(32)), 32) == mask(0x46DD794E)
