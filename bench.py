@@ -11,6 +11,8 @@ inputs.  One JSON line is printed by rank 0 (see the driver contract in the task
   value    videos/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e      videos/s through the public step API with the f32 batch copied from pinned host memory
            every step (double buffered on a copy stream) and the losses + top-20 read back
+  e2e_uint8_input / e2e_tfrecord_input   the same with the quantised uint8 batch a tfrecord holds, and with
+           the batch decoded from a TFRecord shard on disk by the native reader inside the timed loop
   roofline dominant kernel = fused LSTM forward step GEMM of the teacher's lower level, timed alone
   cpu_baseline  the float32 PyTorch-CPU restatement (oracle/, "port": TensorFlow 1.x is not
            installable here) on a bounded sample, on the host's cores
@@ -138,6 +140,59 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _tfrecord_e2e(tr, B, dev, steps, ops):
+    """videos/s of shard files -> reader -> GPU step -> host results (one shard of B synthetic videos, read
+    `steps + warm-up` times; the page cache holds it, as it would hold a training set's hot shards)."""
+    import tempfile
+    import torch
+    from efficientvideoclassification_youtube8m_b200 import readers as R
+    rng = np.random.default_rng(77)
+    tmp = tempfile.mkdtemp(prefix="evc_bench_")
+    path = os.path.join(tmp, "train0.tfrecord")
+    recs = []
+    for i in range(B):
+        recs.append(R.make_sequence_example(
+            f"v{i}", sorted(rng.choice(4716, size=3, replace=False).tolist()),
+            {"rgb": rng.integers(0, 256, size=(300, 1024), dtype=np.uint8),
+             "audio": rng.integers(0, 256, size=(300, 128), dtype=np.uint8)}))
+    R.write_tfrecord(path, recs, with_crc=True)
+    warm = 2
+    rd = R.YT8MFrameFeatureReader(feature_names=["rgb", "audio"], feature_sizes=[1024, 128])
+    it = rd.batches([path] * (steps + warm), B, native=True, verify_crc=True, prefetch=2)
+    xq = torch.empty(B, 300, 1152, dtype=torch.uint8, device=dev)
+    nfd = torch.empty(B, dtype=torch.int32, device=dev)
+    lab = torch.empty(B, 4716, dtype=torch.bool, device=dev)
+    out_host = torch.empty(tr.losses.numel(), dtype=torch.float32).pin_memory()
+    topk_host = torch.empty(B, 20, dtype=torch.int32).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = 0.0
+    for i, (ids, x, y, nf) in enumerate(it):
+        if i == warm:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+        xq.copy_(x, non_blocking=True)
+        nfd.copy_(nf, non_blocking=True)
+        lab.copy_(y, non_blocking=True)
+        tr.step(xq, nfd, lab)
+        idx, _, _ = ops.topk(tr.s_eng.pred, 20)
+        out_host.copy_(tr.losses, non_blocking=True)
+        topk_host.copy_(idx, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    try:
+        os.remove(path)
+        os.rmdir(tmp)
+    except OSError:
+        pass
+    return {"value": B / (ms * 1e-3), "unit": "videos/s", "ms_per_step": ms, "wall_ms_per_step": wall_ms,
+            "shard_bytes_per_step": B * 300 * 1152, "reader": "libevc_reader, CRC32C verified, prefetch 2",
+            "reader_threads": os.cpu_count()}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -259,6 +314,16 @@ def run_ours(args):
     h2d = host_x[0].numel() * 4 + host_nf.numel() * 4 + host_lab.numel()
     d2h = out_host.numel() * 4 + topk_host.numel() * 4
 
+    # ---------------- the whole input path: TFRecord shards on disk -> native reader (libevc_reader, uint8
+    # batches decoded into pinned memory on a background thread) -> H2D -> step -> results on the host.
+    # Extra information only: a failure here must not cost the bench line.
+    e2e_tfrecord = None
+    if world == 1 and not finetune and not args.skip_tfrecord:
+        try:
+            e2e_tfrecord = _tfrecord_e2e(tr, B, dev, max(3, args.steps // 2), ops)
+        except Exception as e:   # noqa: BLE001
+            e2e_tfrecord = {"error": f"{type(e).__name__}: {e}"}
+
     # ---------------- dominant kernel alone: RNN_L1 cell-0 forward steps of the teacher (15 launches; the
     # student's 6 for the fine-tune workload)
     t = tr.s_eng if finetune else tr.t_eng
@@ -324,6 +389,7 @@ def run_ours(args):
             "e2e_uint8_input": {"value": world * B / (ms_e2e_u8 * 1e-3), "unit": "videos/s",
                                 "h2d_bytes_per_step": hq.numel() + host_nf.numel() * 4 + host_lab.numel(),
                                 "ms_per_step": ms_e2e_u8},
+            "e2e_tfrecord_input": e2e_tfrecord,
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roof, "losses": losses,
         }
@@ -350,6 +416,7 @@ def main():
     ap.add_argument("--workload", default="ts_train", choices=["ts_train", "finetune_cfg4"])
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-infer", action="store_true")
+    ap.add_argument("--skip-tfrecord", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
