@@ -320,6 +320,36 @@ class YT8MFrameFeatureReader(BaseReader):
             yield emit()
 
 
+def get_input_data_batches(reader: "YT8MFrameFeatureReader", data_pattern: str, batch_size: int = 1000,
+                           num_epochs: Optional[int] = None, shuffle: bool = True, seed: int = 0,
+                           rank: int = 0, world: int = 1, **batch_kwargs):
+    """train.py:125-175 `get_input_data_tensors` as a generator of host batches: glob the pattern (IOError with
+    the reference's message when nothing matches), shuffle the FILE order every epoch
+    (`string_input_producer(files, num_epochs, shuffle=True)`), run `num_epochs` passes (None = forever) and
+    yield `reader.batches(...)` tuples; the last batch of an epoch may be smaller
+    (`allow_smaller_final_batch=True`).  The example-level mixing of `shuffle_batch_join` (a random queue of
+    50 batches) is not reproduced: videos keep their order inside a shard.
+    rank/world: data-parallel ranks read disjoint, equally long slices of the (shuffled) file list; files that
+    do not divide evenly are dropped from the epoch so that every rank sees the same number of shards."""
+    import glob
+    files = sorted(glob.glob(data_pattern))
+    if not files:
+        raise IOError("Unable to find training files. data_pattern='" + data_pattern + "'.")
+    if world > 1 and len(files) < world:
+        raise IOError(f"{len(files)} shards cannot be split over {world} ranks")
+    epoch = 0
+    while num_epochs is None or epoch < num_epochs:
+        order = list(files)
+        if shuffle:
+            np.random.default_rng(seed + epoch).shuffle(order)      # same permutation on every rank
+        if world > 1:
+            per = len(order) // world
+            order = order[rank * per:(rank + 1) * per]
+        for batch in reader.batches(order, batch_size, **batch_kwargs):
+            yield batch
+        epoch += 1
+
+
 def _prefetched(it, depth):
     """Runs the iterator `it` on a background thread, `depth` items ahead."""
     q: "queue.Queue" = queue.Queue(maxsize=depth)

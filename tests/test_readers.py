@@ -206,3 +206,34 @@ def test_masked_crc32c_known_answers():
     assert lib.evc_crc32c_masked(bytes(32), 32) == mask(0x8A9136AA)
     assert lib.evc_crc32c_masked(bytes([0xFF] * 32), 32) == mask(0x62A8AB43)
     assert lib.evc_crc32c_masked(bytes(range(32)), 32) == mask(0x46DD794E)
+
+
+def test_get_input_data_batches_epochs_shuffle_and_rank_slices(tmp_path):
+    """train.py:125-175: glob + IOError message, per-epoch file shuffle, num_epochs, smaller final batch; ranks
+    read disjoint equal slices of the same permutation."""
+    from efficientvideoclassification_youtube8m_b200 import readers
+    rng = np.random.default_rng(9)
+    for k in range(5):
+        recs = [readers.make_sequence_example(f"s{k}v{i}", [k], _video(rng, 2, [("rgb", 8)])) for i in range(3)]
+        readers.write_tfrecord(str(tmp_path / f"train{k}.tfrecord"), recs)
+    rd = readers.YT8MFrameFeatureReader(num_classes=10, feature_sizes=[8], feature_names=["rgb"])
+    pat = str(tmp_path / "train*.tfrecord")
+    with pytest.raises(IOError, match="Unable to find training files. data_pattern="):
+        next(readers.get_input_data_batches(rd, str(tmp_path / "nothing*")))
+    ep = [b[0] for b in readers.get_input_data_batches(rd, pat, 4, num_epochs=2, pin_memory=False)]
+    assert [len(b) for b in ep] == [4, 4, 4, 3, 4, 4, 4, 3]            # 15 videos per epoch
+    e1, e2 = sum(ep[:4], []), sum(ep[4:], [])
+    assert sorted(e1) == sorted(e2) and len(set(e1)) == 15 and e1 != e2      # reshuffled files, same videos
+    for e in (e1, e2):                                                      # order inside a shard is kept
+        for k in range(5):
+            assert [v for v in e if v.startswith(f"s{k}")] == [f"s{k}v{i}" for i in range(3)]
+    plain = sum((b[0] for b in readers.get_input_data_batches(rd, pat, 4, num_epochs=1, shuffle=False,
+                                                               pin_memory=False)), [])
+    assert plain == [f"s{k}v{i}" for k in range(5) for i in range(3)]
+    seen = []
+    for rank in range(2):
+        ids = sum((b[0] for b in readers.get_input_data_batches(rd, pat, 4, num_epochs=1, rank=rank, world=2,
+                                                                 pin_memory=False)), [])
+        assert len(ids) == 6                                                # 2 of the 5 shards each, 1 dropped
+        seen.append(set(ids))
+    assert not (seen[0] & seen[1])
