@@ -47,10 +47,12 @@ def _as_u8(labels: torch.Tensor) -> torch.Tensor:
 class _Base:
     def __init__(self, cfg: ModelConfig, batch_size: int, device, every_n: int, num_inputs_L1: int,
                  base_learning_rate: float, clip_gradient_norm: float, regularization_penalty: float,
-                 shard_optimizer: Optional[bool] = None):
+                 shard_optimizer: Optional[bool] = None, learning_rate_decay: float = 1.0,
+                 learning_rate_decay_examples: float = 4000000.0):
         self.cfg, self.B, self.device = cfg, batch_size, torch.device(device)
         self.every_n, self.num_inputs_L1 = every_n, num_inputs_L1
-        self.lr, self.clip, self.penalty = base_learning_rate, clip_gradient_norm, regularization_penalty
+        self.base_lr, self.clip, self.penalty = base_learning_rate, clip_gradient_norm, regularization_penalty
+        self.lr_decay, self.lr_decay_examples = learning_rate_decay, learning_rate_decay_examples
         idx = uniform_frame_indices(every_n)
         if len(idx) % num_inputs_L1 != 0:
             raise ValueError(f"every_n={every_n}: {len(idx)} sampled frames do not split into "
@@ -68,6 +70,17 @@ class _Base:
     @staticmethod
     def _world():
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    @property
+    def lr(self) -> float:
+        """tf.train.exponential_decay(base_learning_rate, global_step * batch_size, learning_rate_decay_examples,
+        learning_rate_decay, staircase=True) (train.py:222-236; the flag defaults -- decay 1 -- keep it constant).
+        global_step counts train ops (two per joint iteration); batch_size is the global batch of
+        the data-parallel job."""
+        if self.lr_decay == 1.0:
+            return self.base_lr
+        examples = self.global_step * self.B * self._world()
+        return self.base_lr * self.lr_decay ** float(int(examples / self.lr_decay_examples))
 
     def _allreduce(self, params, lo: int = 0, hi: Optional[int] = None):
         """Average (a slice of) the flat gradient buffer over the data-parallel ranks.  With NCCL the
@@ -180,9 +193,11 @@ class TeacherStudentTrainer(_Base):
                  every_n: int = 10, num_inputs_to_lstm: int = 20, num_inputs_L1: int = 5,
                  base_learning_rate: float = 1e-3, clip_gradient_norm: float = 1.0,
                  regularization_penalty: float = 2.0, teacher_seed: Optional[int] = 0,
-                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None):
+                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None,
+                 learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
-                         clip_gradient_norm, regularization_penalty, shard_optimizer)
+                         clip_gradient_norm, regularization_penalty, shard_optimizer, learning_rate_decay,
+                         learning_rate_decay_examples)
         self.teacher = HLstmParams("model", cfg, device, teacher_seed, lstm_gain)
         self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
         self.t_eng = HLstmEngine(self.teacher, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=True)
@@ -322,9 +337,11 @@ class StudentFinetuneTrainer(_Base):
     def __init__(self, cfg: ModelConfig = ModelConfig(), batch_size: int = 256, device="cuda",
                  every_n: int = 10, num_inputs_L1: int = 5, base_learning_rate: float = 1e-3,
                  clip_gradient_norm: float = 1.0, regularization_penalty: float = 2.0,
-                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None):
+                 student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None,
+                 learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
-                         clip_gradient_norm, regularization_penalty, shard_optimizer)
+                         clip_gradient_norm, regularization_penalty, shard_optimizer, learning_rate_decay,
+                         learning_rate_decay_examples)
         self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
         self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
         self.rows = torch.zeros(1, batch_size, dtype=torch.float32, device=self.device)

@@ -176,3 +176,20 @@ def test_reader_library_exports_every_declared_symbol():
     assert lib.evc_reader_open(None, 0, None, None, 0, 10, 300, 1, 0) is None
     assert b"feature_names is empty" in lib.evc_reader_last_error()
     assert lib.evc_reader_next(None, 4, None, None, None, None, 0) == -1
+
+
+def test_learning_rate_schedule_follows_exponential_decay_staircase():
+    """train.py:222-236: lr = base * decay ** floor(global_step * batch_size / decay_examples); the flag defaults
+    (decay 1) keep it constant.  global_step counts train ops: +2 per joint iteration."""
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import _Base
+    from efficientvideoclassification_youtube8m_b200.train_ops import exponential_decay
+    b = _Base(ModelConfig(), 256, "cpu", 10, 5, 1e-3, 1.0, 2.0)
+    b.global_step = 10 ** 6
+    assert b.lr == 1e-3
+    b = _Base(ModelConfig(), 256, "cpu", 10, 5, 1e-3, 1.0, 2.0, learning_rate_decay=0.95,
+              learning_rate_decay_examples=1000.0)
+    for step, power in ((0, 0), (2, 0), (4, 1), (6, 1), (8, 2), (40, 10)):
+        b.global_step = step
+        assert b.lr == pytest.approx(1e-3 * 0.95 ** power, rel=1e-12)
+        assert b.lr == pytest.approx(exponential_decay(1e-3, step * 256, 1000.0, 0.95), rel=1e-12)
