@@ -3,7 +3,7 @@ hand-written sm_100a kernels on the current CUDA stream; nothing here computes o
 or through torch operators."""
 from __future__ import annotations
 
-from typing import Optional
+from typing import Optional  # noqa: F401
 
 import torch
 
