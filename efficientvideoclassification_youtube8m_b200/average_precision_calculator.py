@@ -106,3 +106,56 @@ class MeanAveragePrecisionCalculator(object):
 
     def peek_map_at_n(self):
         return [c.peek_ap_at_n() for c in self._ap_calculators]
+
+
+class SparseMeanAveragePrecisionCalculator(object):
+    """MeanAveragePrecisionCalculator fed with sparse (class, prediction, label) triplets instead of one python
+    list per class: the same per-class AP (same stable tie order: arrival order inside a class), computed
+    with one sort over all triplets instead of a python loop over 4716 calculators per batch."""
+
+    def __init__(self, num_class):
+        if not isinstance(num_class, int) or num_class <= 1:
+            raise ValueError("num_class must be a positive integer.")
+        self._num_class = num_class
+        self.clear()
+
+    def clear(self):
+        self._cls, self._pred, self._act = [], [], []
+        self._total_positives = np.zeros(self._num_class, dtype=np.float64)
+
+    def is_empty(self):
+        return sum(len(c) for c in self._cls) == 0
+
+    def accumulate(self, classes, predictions, actuals, num_positives):
+        """classes/predictions/actuals: flat arrays of equal length (arrival order); num_positives [num_class]."""
+        classes = np.asarray(classes).reshape(-1).astype(np.int64)
+        predictions = np.asarray(predictions, dtype=np.float64).reshape(-1)
+        actuals = np.asarray(actuals, dtype=np.float64).reshape(-1)
+        if not (len(classes) == len(predictions) == len(actuals)):
+            raise ValueError("the shape of predictions and actuals does not match.")
+        num_positives = np.asarray(num_positives, dtype=np.float64).reshape(-1)
+        if len(num_positives) != self._num_class or np.any(num_positives < 0):
+            raise ValueError("'num_positives' must hold one non-negative count per class.")
+        self._cls.append(classes)
+        self._pred.append(predictions)
+        self._act.append(actuals)
+        self._total_positives += num_positives
+
+    def peek_map_at_n(self):
+        aps = np.zeros(self._num_class, dtype=np.float64)
+        if self.is_empty():
+            return aps.tolist()
+        c, p, a = np.concatenate(self._cls), np.concatenate(self._pred), np.concatenate(self._act)
+        self._cls, self._pred, self._act = [c], [p], [a]
+        order = np.lexsort((-p, c))                      # by class, then prediction descending; stable
+        c, hits = c[order], a[order] > 0
+        start = np.flatnonzero(np.r_[True, c[1:] != c[:-1]])          # first triplet of every class present
+        seg = np.cumsum(np.r_[True, c[1:] != c[:-1]]) - 1
+        rank = np.arange(len(c)) - start[seg] + 1
+        cum = np.cumsum(hits)
+        poscount = cum - (cum[start] - hits[start])[seg]              # positives so far inside the class
+        contrib = np.where(hits, poscount / rank, 0.0)
+        sums = np.bincount(c, weights=contrib, minlength=self._num_class)
+        ok = self._total_positives > 0
+        aps[ok] = sums[ok] / self._total_positives[ok]
+        return aps.tolist()
