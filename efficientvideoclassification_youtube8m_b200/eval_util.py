@@ -48,13 +48,20 @@ def calculate_precision_at_equal_recall_rate(predictions, actuals):
     if kmax == 0:
         return 0.0
     _, val, lab = top_k_device(p, a, kmax)
-    agg = 0.0
-    for row in range(p.shape[0]):
-        n = int(num_labels[row])
-        if n == 0:
-            continue                      # argpartition(p, -0)[-0:] = all classes, no label set -> 0
-        agg += float(np.sum(lab[row, :n][val[row, :n] > 0])) / n
-    return agg / p.shape[0]
+    return perr_from_top_k(val, lab, num_labels)
+
+
+def perr_from_top_k(val, lab, num_labels):
+    """eval_util.py:43-59 given every video's top-max(num_labels) predictions (descending) and their labels:
+    mean over videos of |{top-num_labels predictions that are > 0 and labelled}| / num_labels; a video without
+    labels contributes 0 (argpartition(p, -0)[-0:] is every class and no label is set)."""
+    val, lab = np.asarray(val), np.asarray(lab, dtype=np.float64)
+    num_labels = np.asarray(num_labels, dtype=np.int64)
+    if val.shape[0] == 0:
+        return 0.0
+    within = np.arange(val.shape[1])[None, :] < num_labels[:, None]
+    hits = np.sum(lab * (val > 0) * within, axis=1)
+    return float(np.sum(hits[num_labels > 0] / num_labels[num_labels > 0]) / val.shape[0])
 
 
 def top_k_triplets(predictions, labels, k=20):
