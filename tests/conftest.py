@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_libraries():
+    """Both in-tree libraries (libevc.so: nvcc cross-compiles without a GPU; libevc_reader.so: g++) exist before
+    any test imports the package; a no-op when they are newer than their sources."""
+    import __graft_entry__ as g
+    g.build()
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
