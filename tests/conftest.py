@@ -17,7 +17,11 @@ def _built_libraries():
     """Both in-tree libraries (libevc.so: nvcc cross-compiles without a GPU; libevc_reader.so: g++) exist before
     any test imports the package; a no-op when they are newer than their sources."""
     import __graft_entry__ as g
-    g.build()
+    try:
+        g.build()
+    except Exception:                     # e.g. no compiler on this machine: prebuilt in-tree libraries still serve
+        if not (os.path.exists(g.LIB) and os.path.exists(g.READER_LIB)):
+            raise
 
 
 def pytest_collection_modifyitems(config, items):
