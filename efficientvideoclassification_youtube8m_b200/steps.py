@@ -15,6 +15,7 @@ flat gradient buffer before the per-variable clip + Adam.
 from __future__ import annotations
 
 import os
+import time
 from typing import Dict, Optional
 
 import torch
@@ -412,11 +413,50 @@ class TeacherEvaluator(_Base):
         self.teacher = params
         self.t_eng = HLstmEngine(params, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=False)
         self.top_k = top_k
+        self.rows = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
 
     def step(self, model_input_raw, num_frames, labels=None):
+        """Returns (predictions [B,V], top-k idx, top-k values, top-k labels|None); CE rows in self.rows."""
         self._check(model_input_raw, num_frames, labels)
         t = self.t_eng
         t.forward(model_input_raw, None, True, num_frames, num_frames)
         lab = _as_u8(labels) if labels is not None else None
+        if lab is not None:
+            ops.ce_kl_loss(t.pred, None, lab, 1.0, 0.0, self.rows, None, None)
         idx, val, tl = ops.topk(t.pred, self.top_k, lab)
         return t.pred, idx, val, tl
+
+
+def evaluation_loop(evaluator, batches, metrics, log=None) -> Dict[str, object]:
+    """The `while not coord.should_stop()` loop of eval_finetune.py:240-275 / validate.py:255-290: run every
+    batch of `batches` (tuples of `readers.*.batches`) through `evaluator.step`, fold predictions, labels and the
+    per-video cross-entropy into `metrics` (eval_util.EvaluationMetrics, optionally distributed) and return the
+    epoch dictionary of `metrics.get()` plus `examples_processed` and the mean `examples_per_second`.
+
+    The execution plan has a fixed batch size: the epoch's last, smaller batch is padded with empty videos
+    (num_frames = 0, no labels) whose rows are dropped before they reach the metrics."""
+    B, dev = evaluator.B, evaluator.device
+    metrics.clear()
+    examples, rates = 0, []
+    for ids, x, y, nf in batches:
+        t0 = time.time()
+        n = int(x.shape[0])
+        if n > B:
+            raise ValueError(f"batch of {n} videos exceeds the evaluator's plan ({B})")
+        if n < B:
+            x = torch.cat([x, x.new_zeros((B - n,) + tuple(x.shape[1:]))])
+            y = torch.cat([y, y.new_zeros((B - n,) + tuple(y.shape[1:]))])
+            nf = torch.cat([nf, nf.new_zeros(B - n)])
+        xd, yd, nd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), nf.to(dev, non_blocking=True)
+        pred = evaluator.step(xd, nd, yd)[0]
+        info = metrics.accumulate(pred[:n], yd[:n], evaluator.rows[:n])
+        dt = max(time.time() - t0, 1e-9)
+        examples += n
+        rates.append(n / dt)
+        if log is not None:
+            info = dict(info, examples_per_second=n / dt)
+            log("examples_processed: %d | %s" % (examples, " | ".join(f"{k}: {v:.4g}" for k, v in info.items())))
+    out = dict(metrics.get())
+    out["examples_processed"] = examples
+    out["examples_per_second"] = float(sum(rates) / len(rates)) if rates else 0.0
+    return out

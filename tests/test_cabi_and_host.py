@@ -193,3 +193,50 @@ def test_learning_rate_schedule_follows_exponential_decay_staircase():
         b.global_step = step
         assert b.lr == pytest.approx(1e-3 * 0.95 ** power, rel=1e-12)
         assert b.lr == pytest.approx(exponential_decay(1e-3, step * 256, 1000.0, 0.95), rel=1e-12)
+
+
+def test_evaluation_loop_pads_the_last_batch_and_drops_the_padding():
+    """steps.evaluation_loop (eval_finetune.py:240-275) with stand-ins for the evaluator and the metrics: the
+    plan's batch size is fixed, so the epoch's last batch is padded with empty videos whose rows never reach
+    the metrics."""
+    import torch
+    from efficientvideoclassification_youtube8m_b200.steps import evaluation_loop
+
+    class Evaluator:
+        B, device = 4, torch.device("cpu")
+
+        def __init__(self):
+            self.seen = []
+
+        def step(self, x, nf, y):
+            assert x.shape[0] == self.B and nf.shape[0] == self.B and y.shape[0] == self.B
+            self.seen.append(nf.tolist())
+            self.rows = x.float().sum(dim=(1, 2))
+            return x.float().mean(dim=1), None, None, None
+
+    class Metrics:
+        def __init__(self):
+            self.calls, self.cleared = [], 0
+
+        def clear(self):
+            self.cleared += 1
+
+        def accumulate(self, p, y, loss):
+            self.calls.append((p.shape[0], y.shape[0], loss.shape[0], float(loss.sum())))
+            return {"hit_at_one": 1.0, "perr": 0.5, "loss": float(loss.mean())}
+
+        def get(self):
+            return {"gap": 0.25, "avg_loss": 1.0}
+
+    batches = [(["a", "b", "c", "d"], torch.ones(4, 3, 2, dtype=torch.uint8), torch.zeros(4, 5, dtype=torch.bool),
+                torch.tensor([3, 2, 1, 3], dtype=torch.int32)),
+               (["e"], torch.full((1, 3, 2), 2, dtype=torch.uint8), torch.ones(1, 5, dtype=torch.bool),
+                torch.tensor([2], dtype=torch.int32))]
+    ev, m, lines = Evaluator(), Metrics(), []
+    out = evaluation_loop(ev, batches, m, log=lines.append)
+    assert m.cleared == 1 and ev.seen == [[3, 2, 1, 3], [2, 0, 0, 0]]
+    assert m.calls == [(4, 4, 4, 24.0), (1, 1, 1, 12.0)]
+    assert out["gap"] == 0.25 and out["examples_processed"] == 5 and out["examples_per_second"] > 0
+    assert len(lines) == 2 and lines[1].startswith("examples_processed: 5 | hit_at_one: 1")
+    with pytest.raises(ValueError, match="exceeds"):
+        evaluation_loop(ev, [(["x"] * 5, torch.ones(5, 3, 2), torch.zeros(5, 5), torch.zeros(5, dtype=torch.int32))], m)
