@@ -24,6 +24,8 @@ SIGNATURES = {
     "evc_lstm_lengths": [P, I, I, I, I, P, P, P],
     "evc_random_frame_index": [P, P, I, I, P, P],
     "evc_random_sequence_index": [P, P, I, I, P, P],
+    "evc_sampled_lengths": [P, I, I, P, P],
+    "evc_random_uniform": [C.c_ulonglong, C.c_ulonglong, P, L, P],
     "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
     "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
     "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P],
@@ -80,9 +82,12 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def stream():
+def stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device).  The library is used
+    by one process per GPU with `torch.cuda.set_device(local_rank)` called first (bench.py, the launchers):
+    kernels run on the CURRENT device, so tensors of another device are rejected by `ops._cuda`."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def launch_count() -> int:

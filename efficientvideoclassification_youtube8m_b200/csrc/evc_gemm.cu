@@ -119,12 +119,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
                   const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, CS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
-    configured = true;
-  }
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles_mc = (args.tiles_m + CS - 1) / CS;
   const int work = tiles_mc * args.tiles_n * args.split_k;
   if (work <= 0) return EVC_OK;
@@ -331,12 +326,8 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
       a.c_all = c_all; a.h_all = hb; a.gates_all = gb;
       a.slabs = static_cast<float*>(workspace);
       a.barrier = bar;
-      static bool configured = false;
-      if (!configured) {
-        e = cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(lstm_rec_fwd)");
-        configured = true;
-      }
+      rc = opt_in_smem(reinterpret_cast<const void*>(lstm_rec_fwd_kernel), GemmCfg<256>::SMEM_BYTES);
+      if (rc) return rc;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(tiles * S);
       cfg.blockDim = dim3(GEMM_THREADS);

@@ -3,6 +3,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace evc {
 
@@ -23,15 +26,33 @@ int check_launch(const char* what) {
   return EVC_OK;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// Per-device state (a process may drive several devices, one host thread each): the SM count and the
+// shared-memory opt-in of every kernel are looked up by the CURRENT device of the calling thread.
+constexpr int kMaxDevices = 64;
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+int opt_in_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({func, dev})) return EVC_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  done.insert({func, dev});
+  return EVC_OK;
 }
 
 }  // namespace evc

@@ -13,7 +13,8 @@ int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 int check_launch(const char* what);  // cudaGetLastError() -> EVC code
 void count_launch();
-int num_sms();
+int num_sms();                                      // of the calling thread's current device
+int opt_in_smem(const void* func, int bytes);       // once per (kernel, device): MaxDynamicSharedMemorySize
 // elementwise BasicLSTM cell kernels (evc_kernels.cu) used by the split-K recurrence paths
 int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, const float* bias, const float* c_prev,
                          const void* h_prev, const int* seq_len, int t, int rows, int H, float* c_out, void* h_out,

@@ -187,7 +187,8 @@ __global__ void random_frame_index_kernel(const float* __restrict__ u, const int
   PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
-  idx[i] = static_cast<int>(__fmul_rn(u[i], static_cast<float>(nf[i / K])));
+  // (a video with num_frames = 0 yields index 0: the zero-padded first frame, never an address before the row)
+  idx[i] = max(static_cast<int>(__fmul_rn(u[i], static_cast<float>(nf[i / K]))), 0);
 }
 // model_utils.py:23-33  start = int32(u*float32(max(n-K,0)+1)); idx = min(start+k, n-1)
 __global__ void random_sequence_index_kernel(const float* __restrict__ u, const int* __restrict__ nf, int B, int K,
@@ -199,7 +200,40 @@ __global__ void random_sequence_index_kernel(const float* __restrict__ u, const 
   const int n = nf[b];
   const int ms = max(n - K, 0);
   const int start = static_cast<int>(__fmul_rn(u[b], static_cast<float>(ms + 1)));
-  idx[i] = min(start + k, n - 1);
+  idx[i] = max(min(start + k, n - 1), 0);   // n = 0 (empty video): the reference's -1 would address before the row
+}
+
+__global__ void sampled_lengths_kernel(const int* __restrict__ nf, int B, int K, long long* __restrict__ out) {
+  PDL_PROLOGUE();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = nf[b] > 0 ? K : 0;
+}
+
+// tf.random_uniform([..], dtype=float32) of the samplers (model_utils.py:25-27,50-51): Philox4x32-10 counter-based
+// generator [TF random_distributions.h PhiloxRandom], 4 floats per counter, converted the way TF's
+// Uint32ToFloat does (23 random mantissa bits -> [1,2) - 1 = [0,1)).  The stream is a pure function of
+// (seed, offset + element index); TF's own keys/counters derive from graph-level seeds and are not reproduced.
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__global__ void random_uniform_kernel(unsigned long long seed, unsigned long long offset, float* __restrict__ out,
+                                      long long n) {
+  PDL_PROLOGUE();
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // group of 4 outputs
+  if (q * 4 >= n) return;
+  const unsigned long long ctr = offset + static_cast<unsigned long long>(q);
+  uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (q * 4 + j < n) out[q * 4 + j] = __uint_as_float((127u << 23) | (c[j] & 0x7FFFFFu)) - 1.0f;
 }
 
 // MultiRNNCell(state_is_tuple=False) state = [c0|h0|c1|h1]: gather the final
@@ -841,6 +875,22 @@ extern "C" int evc_random_sequence_index(const float* u, const int* num_frames, 
   return check_launch("random_sequence_index");
 }
 
+extern "C" int evc_sampled_lengths(const int* num_frames, int B, int K, long long* out, void* stream) {
+  pdl_launch(sampled_lengths_kernel, dim3((B + 127) / 128), dim3(128), 0, EVC_STREAM(stream), num_frames, B, K, out);
+  count_launch();
+  return check_launch("sampled_lengths");
+}
+
+extern "C" int evc_random_uniform(unsigned long long seed, unsigned long long offset, float* out, long long n,
+                                  void* stream) {
+  if (n <= 0) return EVC_OK;
+  const long long groups = (n + 3) / 4;
+  pdl_launch(random_uniform_kernel, dim3(static_cast<unsigned>((groups + 127) / 128)), dim3(128), 0, EVC_STREAM(stream),
+             seed, offset, out, n);
+  count_launch();
+  return check_launch("random_uniform");
+}
+
 extern "C" int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,
                               void* out_bf16, float* out_f32, void* stream) {
   const long long n = static_cast<long long>(rows) * H;
@@ -969,11 +1019,7 @@ extern "C" int evc_topk(const float* P, int B, int V, int k, const unsigned char
   if (k > V) return set_error(EVC_ERR_ARG, "topk: k > num_classes (clamp k = min(k, V) on the host)");
   const size_t smem = (static_cast<size_t>(V) + 32) * sizeof(unsigned long long);
   if (smem > 200 * 1024) return set_error(EVC_ERR_UNSUPPORTED, "topk: num_classes too large for one block");
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(topk_kernel), 200 * 1024)) return rc;
   pdl_launch(topk_kernel, dim3(B), dim3(256), smem, EVC_STREAM(stream), P, V, k, labels, idx_out, val_out, lab_out);
   count_launch();
   return check_launch("topk");

@@ -13,9 +13,17 @@ BF16 = torch.bfloat16
 
 
 def _cuda(*ts):
+    cur = None
     for t in ts:
-        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+        if t is None:
+            continue
+        if not t.is_cuda or not t.is_contiguous():
             raise ValueError("libevc operands must be contiguous CUDA tensors")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise ValueError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: the "
+                             "library launches on the current device (call torch.cuda.set_device first)")
 
 
 def pad8(n: int, mult: int = 64) -> int:
@@ -73,21 +81,38 @@ def lstm_lengths(num_frames, num_chunks, chunk_len, len_l1=None, len_l2=None):
     return len_l1, len_l2
 
 
-def random_frame_index(u, num_frames):
-    _cuda(u, num_frames)
+def random_frame_index(u, num_frames, out=None):
+    _cuda(u, num_frames, out)
     B, K = u.shape
-    idx = torch.empty(B, K, dtype=torch.int32, device=u.device)
+    idx = out if out is not None else torch.empty(B, K, dtype=torch.int32, device=u.device)
     check(lib.evc_random_frame_index(ptr(u), ptr(num_frames), B, K, ptr(idx), stream()), "evc_random_frame_index")
     return idx
 
 
-def random_sequence_index(u, num_frames, K):
-    _cuda(u, num_frames)
+def sampled_lengths(num_frames, K, out):
+    """Sequence lengths of the randomly sampled student input: K for a video with frames, 0 for an empty one."""
+    _cuda(num_frames, out)
+    assert num_frames.dtype == torch.int32 and out.dtype == torch.int64
+    check(lib.evc_sampled_lengths(ptr(num_frames), num_frames.shape[0], K, ptr(out), stream()), "evc_sampled_lengths")
+    return out
+
+
+def random_sequence_index(u, num_frames, K, out=None):
+    _cuda(u, num_frames, out)
     B = u.shape[0]
-    idx = torch.empty(B, K, dtype=torch.int32, device=u.device)
+    idx = out if out is not None else torch.empty(B, K, dtype=torch.int32, device=u.device)
     check(lib.evc_random_sequence_index(ptr(u), ptr(num_frames), B, K, ptr(idx), stream()),
           "evc_random_sequence_index")
     return idx
+
+
+def random_uniform(out, seed: int, offset: int = 0):
+    """Fill the f32 tensor `out` with U[0,1) draws of the counter-based Philox stream (seed, offset)."""
+    _cuda(out)
+    assert out.dtype == torch.float32
+    check(lib.evc_random_uniform(int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), ptr(out), out.numel(),
+                                 stream()), "evc_random_uniform")
+    return out
 
 
 def lstm_workspace_bytes(rows, H, Kx):

@@ -151,12 +151,30 @@ class HLstmParams:
             self.w[n].copy_(t.to(torch.float32))
         self.refresh_shadows()
 
+    def _sync_if_stale(self) -> None:
+        """With the optimizer sharded over the data-parallel ranks (the default for world > 1) a rank only updates
+        its own row block of every f32 master matrix; the other rows are refreshed here.  COLLECTIVE: every rank
+        must reach state_dict()/save() together (as in a checkpoint hook that runs on all ranks; let rank 0
+        alone write the file afterwards)."""
+        if not getattr(self, "_master_stale", False):
+            return
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("master weights are sharded over ranks that are gone: call sync_master_weights() "
+                               "before destroying the process group")
+        self.sync_master_weights(dist.get_rank(), dist.get_world_size())
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
+        """name -> f32 tensor (clone).  Collective after sharded updates, see `_sync_if_stale`."""
+        self._sync_if_stale()
         return {n: self.w[n].detach().clone() for n in self.names}
 
-    def save(self, path: str) -> None:
-        """name -> array map of this scope's variables (`.npz`; keys are the TF checkpoint names)."""
-        np.savez(path, **{n: self.w[n].detach().cpu().numpy() for n in self.names})
+    def save(self, path: str, write: bool = True) -> None:
+        """name -> array map of this scope's variables (`.npz`; keys are the TF checkpoint names).  Collective
+        after sharded updates (see `_sync_if_stale`); pass write=(rank == 0) to let one rank write the file."""
+        self._sync_if_stale()
+        if write:
+            np.savez(path, **{n: self.w[n].detach().cpu().numpy() for n in self.names})
 
     def load(self, path: str, from_scope: Optional[str] = None) -> None:
         """Load a name -> array map.  `from_scope` renames `<from_scope>/...` keys to this scope: with

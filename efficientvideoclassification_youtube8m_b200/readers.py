@@ -255,11 +255,15 @@ class YT8MFrameFeatureReader(BaseReader):
         against the protobuf library in tests/test_readers.py)."""
         pin = torch.cuda.is_available() if pin_memory is None else pin_memory
         if native:
-            # prefetch > 0: a ring of prefetch + 2 pinned buffer sets is reused (one being filled, `prefetch`
-            # queued, one in the consumer's hands) -- a batch is valid until the consumer asks for the one after
-            # the next; prefetch = 0 allocates fresh tensors for every batch.
+            # prefetch > 0: a ring of prefetch + 3 pinned buffer sets is reused: one being filled by the worker,
+            # `prefetch` queued, one in the consumer's hands and one more that the consumer handed to the GPU
+            # in the previous iteration.  LIFETIME CONTRACT: the tensors of batch j stay untouched until the
+            # consumer asks for batch j+2, i.e. an asynchronous `x.cuda(non_blocking=True)` of batch j must have
+            # completed by the time the consumer requests batch j+2 (true for any loop that fetches a result of
+            # step j, or synchronises the stream, once per iteration; otherwise record an event after the copy and
+            # wait for it before calling next()).  prefetch = 0 allocates fresh tensors for every batch.
             it = self._native_batches(list(filenames), batch_size, drop_remainder, pin, num_threads, verify_crc,
-                                      ring=prefetch + 2 if prefetch > 0 else 0)
+                                      ring=prefetch + 3 if prefetch > 0 else 0)
             return _prefetched(it, prefetch) if prefetch > 0 else it
         return self._python_batches(filenames, batch_size, drop_remainder, pin)
 
@@ -322,32 +326,68 @@ class YT8MFrameFeatureReader(BaseReader):
 
 def get_input_data_batches(reader: "YT8MFrameFeatureReader", data_pattern: str, batch_size: int = 1000,
                            num_epochs: Optional[int] = None, shuffle: bool = True, seed: int = 0,
-                           rank: int = 0, world: int = 1, **batch_kwargs):
+                           rank: int = 0, world: int = 1, uneven: str = "min", agree=None, **batch_kwargs):
     """train.py:125-175 `get_input_data_tensors` as a generator of host batches: glob the pattern (IOError with
     the reference's message when nothing matches), shuffle the FILE order every epoch
     (`string_input_producer(files, num_epochs, shuffle=True)`), run `num_epochs` passes (None = forever) and
     yield `reader.batches(...)` tuples; the last batch of an epoch may be smaller
     (`allow_smaller_final_batch=True`).  The example-level mixing of `shuffle_batch_join` (a random queue of
     50 batches) is not reproduced: videos keep their order inside a shard.
-    rank/world: data-parallel ranks read disjoint, equally long slices of the (shuffled) file list; files that
-    do not divide evenly are dropped from the epoch so that every rank sees the same number of shards."""
+
+    rank/world: data-parallel ranks read disjoint slices `order[rank::world]` of the (shuffled) file list, so
+    every shard is read by exactly one rank.  YT8M shards hold different numbers of videos, so the ranks would
+    produce different numbers of batches per epoch and the first one to finish would leave the others hanging
+    in the step's collectives.  Before every batch the ranks therefore agree (one tiny all-reduce through
+    `agree`, default: torch.distributed on the default group) on whether the epoch goes on:
+      uneven="min"  the epoch ends for everybody when the first rank runs out (training: the few surplus
+                    videos of the longer ranks are skipped this epoch, the shuffle moves them next epoch);
+      uneven="pad"  the epoch ends when the LAST rank runs out; ranks that ran out yield empty batches
+                    (0 videos, right shapes) so that no video is lost (evaluation: `steps.evaluation_loop`
+                    pads them to the plan's batch size and drops the padding before the metrics)."""
     import glob
     files = sorted(glob.glob(data_pattern))
     if not files:
         raise IOError("Unable to find training files. data_pattern='" + data_pattern + "'.")
-    if world > 1 and len(files) < world:
-        raise IOError(f"{len(files)} shards cannot be split over {world} ranks")
+    if uneven not in ("min", "pad"):
+        raise ValueError("uneven must be 'min' or 'pad'")
+    if world > 1 and agree is None:
+        agree = _dist_agree
+    D, V, T = sum(reader.feature_sizes), reader.num_classes, reader.max_frames
     epoch = 0
     while num_epochs is None or epoch < num_epochs:
         order = list(files)
         if shuffle:
             np.random.default_rng(seed + epoch).shuffle(order)      # same permutation on every rank
         if world > 1:
-            per = len(order) // world
-            order = order[rank * per:(rank + 1) * per]
-        for batch in reader.batches(order, batch_size, **batch_kwargs):
+            order = order[rank::world]
+        it = iter(reader.batches(order, batch_size, **batch_kwargs)) if order else iter(())
+        while True:
+            batch = next(it, None)
+            if world > 1:
+                # have = 1 if this rank still has a batch; min over ranks = everybody has one, max = somebody has
+                everybody, somebody = agree(batch is not None)
+                if uneven == "min" and not everybody:
+                    break
+                if uneven == "pad":
+                    if not somebody:
+                        break
+                    if batch is None:
+                        batch = ([], torch.empty(0, T, D, dtype=torch.uint8), torch.empty(0, V, dtype=torch.bool),
+                                 torch.empty(0, dtype=torch.int32))
+            elif batch is None:
+                break
             yield batch
         epoch += 1
+
+
+def _dist_agree(have: bool):
+    """(all ranks have a batch, some rank has a batch) over the default process group."""
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([1 if have else 0, 0 if have else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    have_n, miss_n = t.tolist()
+    return miss_n == 0, have_n > 0
 
 
 def _prefetched(it, depth):

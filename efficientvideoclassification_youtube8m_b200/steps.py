@@ -26,6 +26,7 @@ from .engine import OVERLAP_OPTIMIZER, OVERLAP_STUDENT, HLstmEngine, overlap_mod
 from .params import HLstmParams, ModelConfig
 
 MAX_FRAMES = 300  # train.py:262
+SAMPLERS = ("uniform", "random_frames", "random_sequence")
 
 
 def uniform_frame_indices(every_n: int):
@@ -49,7 +50,8 @@ class _Base:
     def __init__(self, cfg: ModelConfig, batch_size: int, device, every_n: int, num_inputs_L1: int,
                  base_learning_rate: float, clip_gradient_norm: float, regularization_penalty: float,
                  shard_optimizer: Optional[bool] = None, learning_rate_decay: float = 1.0,
-                 learning_rate_decay_examples: float = 4000000.0):
+                 learning_rate_decay_examples: float = 4000000.0, sampling: str = "uniform",
+                 sampling_seed: int = 0):
         self.cfg, self.B, self.device = cfg, batch_size, torch.device(device)
         self.every_n, self.num_inputs_L1 = every_n, num_inputs_L1
         self.base_lr, self.clip, self.penalty = base_learning_rate, clip_gradient_norm, regularization_penalty
@@ -61,6 +63,17 @@ class _Base:
         self.student_frames = len(idx)
         self.frame_idx = torch.tensor(idx, dtype=torch.int32, device=self.device)
         self.nf_student = torch.zeros(batch_size, dtype=torch.int64, device=self.device)
+        # BASELINE config #5 "random vs uniform": the student's frames drawn by model_utils.SampleRandomFrames
+        # ("random_frames": K independent frames per video, model_utils.py:39-58) or SampleRandomSequence
+        # ("random_sequence": K consecutive frames from a random start, :11-36) instead of every n-th frame.
+        if sampling not in SAMPLERS:
+            raise ValueError(f"sampling must be one of {SAMPLERS}")
+        self.sampling, self.sampling_seed, self._draws = sampling, int(sampling_seed), 0
+        if sampling != "uniform":
+            K = self.student_frames
+            self.u = torch.empty((batch_size, K) if sampling == "random_frames" else (batch_size,),
+                                 dtype=torch.float32, device=self.device)
+            self.frame_idx_rand = torch.empty(batch_size, K, dtype=torch.int32, device=self.device)
         self.global_step = 0
         self._pending = []
         self._gathers = []
@@ -71,6 +84,29 @@ class _Base:
     @staticmethod
     def _world():
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _student_sample(self, num_frames, u=None):
+        """The student's frame indices and sequence lengths for this batch, on the current stream.
+        uniform: every_n-th frame and the float64 length rule (train.py:262-272).
+        random_*: indices from the reference's samplers given U[0,1) draws `u` (parity: pass them; otherwise
+        the library's Philox stream, counter advancing per step); every sampled frame is a real frame of the
+        video (the samplers index inside [0, num_frames)), so the student sees K valid steps -- K * [n > 0]."""
+        if self.sampling == "uniform":
+            ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
+            return self.frame_idx
+        K = self.student_frames
+        if u is None:
+            ops.random_uniform(self.u, self.sampling_seed, self._draws)
+            self._draws += (self.u.numel() + 3) // 4
+            u = self.u
+        elif tuple(u.shape) != tuple(self.u.shape) or u.dtype != torch.float32:
+            raise ValueError(f"u must be float32 {tuple(self.u.shape)} for sampling='{self.sampling}'")
+        if self.sampling == "random_frames":
+            ops.random_frame_index(u, num_frames, out=self.frame_idx_rand)
+        else:
+            ops.random_sequence_index(u, num_frames, K, out=self.frame_idx_rand)
+        ops.sampled_lengths(num_frames, K, self.nf_student)
+        return self.frame_idx_rand
 
     @property
     def lr(self) -> float:
@@ -195,10 +231,11 @@ class TeacherStudentTrainer(_Base):
                  base_learning_rate: float = 1e-3, clip_gradient_norm: float = 1.0,
                  regularization_penalty: float = 2.0, teacher_seed: Optional[int] = 0,
                  student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None,
-                 learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0):
+                 learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0,
+                 sampling: str = "uniform", sampling_seed: int = 0):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
                          clip_gradient_norm, regularization_penalty, shard_optimizer, learning_rate_decay,
-                         learning_rate_decay_examples)
+                         learning_rate_decay_examples, sampling, sampling_seed)
         self.teacher = HLstmParams("model", cfg, device, teacher_seed, lstm_gain)
         self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
         self.t_eng = HLstmEngine(self.teacher, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=True)
@@ -215,7 +252,7 @@ class TeacherStudentTrainer(_Base):
                                if (overlap_mode() & OVERLAP_STUDENT) and self.device.type == "cuda" else None)
         self._teacher_ready = torch.cuda.Event() if self.student_stream is not None else None
 
-    def _forward_backward_two_streams(self, raw, num_frames, labels_u8, fuse_optimizer=False):
+    def _forward_backward_two_streams(self, raw, num_frames, labels_u8, fuse_optimizer=False, u=None):
         B = self.B
         t, s = self.t_eng, self.s_eng
         main, side = torch.cuda.current_stream(), self.student_stream
@@ -224,8 +261,8 @@ class TeacherStudentTrainer(_Base):
         # kernels should be in the queue before the student's small ones)
         t.forward(raw, None, True, num_frames, num_frames, mix=False)
         with torch.cuda.stream(side):
-            ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-            s.forward(raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
+            idx = self._student_sample(num_frames, u)
+            s.forward(raw, idx, True, self.nf_student, num_frames, mix=False)
         t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
         self._teacher_ready.record(main)             # t.state and t.pred are final
         with torch.cuda.stream(side):
@@ -254,22 +291,22 @@ class TeacherStudentTrainer(_Base):
             ops.reduce_rows(self.rows[2], 1.0, self.losses[2:3])
             ops.reduce_rows(self.rows[3], 1.0 / B, self.losses[3:4])
 
-    def forward_backward(self, raw, num_frames, labels_u8):
+    def forward_backward(self, raw, num_frames, labels_u8, u=None):
         """Losses and gradients of both models (complete on the current stream when this returns)."""
-        self._forward_backward(raw, num_frames, labels_u8)
+        self._forward_backward(raw, num_frames, labels_u8, u=u)
         if self.student_stream is not None:
             torch.cuda.current_stream().wait_stream(self.student_stream)
 
-    def _forward_backward(self, raw, num_frames, labels_u8, fuse_optimizer=False):
+    def _forward_backward(self, raw, num_frames, labels_u8, fuse_optimizer=False, u=None):
         if self.student_stream is not None:
-            return self._forward_backward_two_streams(raw, num_frames, labels_u8, fuse_optimizer)
+            return self._forward_backward_two_streams(raw, num_frames, labels_u8, fuse_optimizer, u)
         B = self.B
         t, s = self.t_eng, self.s_eng
         # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
         t.forward(raw, None, True, num_frames, num_frames, mix=False)
-        # student: every_n-th frame, float64 length rule (train.py:262-272,349-357)
-        ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
+        # student: every_n-th frame, float64 length rule (train.py:262-272,349-357) -- or a random sampler
+        idx = self._student_sample(num_frames, u)
+        s.forward(raw, idx, True, self.nf_student, num_frames, mix=False)
         # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term.
         # One launch: mixture, CE rows and the gradients w.r.t. the logits.
         t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
@@ -302,16 +339,16 @@ class TeacherStudentTrainer(_Base):
             self._apply(self.student)
         self._finish_gathers()
 
-    def step(self, model_input_raw, num_frames, labels) -> None:
+    def step(self, model_input_raw, num_frames, labels, u=None) -> None:
         """One iteration = both train ops (global_step += 2).  Asynchronous; read
-        results with :meth:`fetch`."""
+        results with :meth:`fetch`.  u: the random samplers' U[0,1) draws (sampling != "uniform", parity runs)."""
         self._check(model_input_raw, num_frames, labels)
         if self.student_stream is not None and self._early_apply_ok():
             # optimizer passes are issued inside the schedule, each as soon as its gradients are final
-            self._forward_backward(model_input_raw, num_frames, _as_u8(labels), fuse_optimizer=True)
+            self._forward_backward(model_input_raw, num_frames, _as_u8(labels), fuse_optimizer=True, u=u)
             torch.cuda.current_stream().wait_stream(self.student_stream)
         else:
-            self._forward_backward(model_input_raw, num_frames, _as_u8(labels))
+            self._forward_backward(model_input_raw, num_frames, _as_u8(labels), u=u)
             self.apply_gradients()
         self.global_step += 2
 
@@ -339,20 +376,21 @@ class StudentFinetuneTrainer(_Base):
                  every_n: int = 10, num_inputs_L1: int = 5, base_learning_rate: float = 1e-3,
                  clip_gradient_norm: float = 1.0, regularization_penalty: float = 2.0,
                  student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None,
-                 learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0):
+                 learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0,
+                 sampling: str = "uniform", sampling_seed: int = 0):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
                          clip_gradient_norm, regularization_penalty, shard_optimizer, learning_rate_decay,
-                         learning_rate_decay_examples)
+                         learning_rate_decay_examples, sampling, sampling_seed)
         self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
         self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
         self.rows = torch.zeros(1, batch_size, dtype=torch.float32, device=self.device)
         self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)
 
-    def step(self, model_input_raw, num_frames, labels) -> None:
+    def step(self, model_input_raw, num_frames, labels, u=None) -> None:
         self._check(model_input_raw, num_frames, labels)
         B, s = self.B, self.s_eng
-        ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames, mix=False)
+        idx = self._student_sample(num_frames, u)
+        s.forward(model_input_raw, idx, True, self.nf_student, num_frames, mix=False)
         s.classifier_loss_fused(_as_u8(labels), None, 1.0 / B, 0.0, self.rows[0], None)
         s.classifier_backward(None, logits_done=True)
         self._reduce_grads(self.student, self.student.names[8:])
@@ -384,19 +422,20 @@ class StudentEvaluator(_Base):
     """Student-only inference + top-k (eval_finetune.py:108-175, run_eval.sh)."""
 
     def __init__(self, params: HLstmParams, batch_size: int, every_n: int = 10, num_inputs_L1: int = 5,
-                 top_k: int = 20):
-        super().__init__(params.cfg, batch_size, params.device, every_n, num_inputs_L1, 0.0, 0.0, 0.0)
+                 top_k: int = 20, sampling: str = "uniform", sampling_seed: int = 0):
+        super().__init__(params.cfg, batch_size, params.device, every_n, num_inputs_L1, 0.0, 0.0, 0.0,
+                         sampling=sampling, sampling_seed=sampling_seed)
         self.student = params
         self.s_eng = HLstmEngine(params, batch_size, self.student_frames, num_inputs_L1, training=False)
         self.top_k = top_k
         self.rows = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
 
-    def step(self, model_input_raw, num_frames, labels=None):
+    def step(self, model_input_raw, num_frames, labels=None, u=None):
         """Returns (predictions [B,V], top-k idx, top-k values, top-k labels|None); CE rows in self.rows."""
         self._check(model_input_raw, num_frames, labels)
         s = self.s_eng
-        ops.num_frames_student(num_frames, self.every_n, MAX_FRAMES, self.nf_student)
-        s.forward(model_input_raw, self.frame_idx, True, self.nf_student, num_frames)
+        idx = self._student_sample(num_frames, u)
+        s.forward(model_input_raw, idx, True, self.nf_student, num_frames)
         lab = _as_u8(labels) if labels is not None else None
         if lab is not None:
             ops.ce_kl_loss(s.pred, None, lab, 1.0, 0.0, self.rows, None, None)
@@ -427,6 +466,57 @@ class TeacherEvaluator(_Base):
         return t.pred, idx, val, tl
 
 
+class TeacherStudentEvaluator(_Base):
+    """Teacher + student inference of validate.py:109-189 (run_validate.sh): the teacher on all 300 frames under
+    scope "model", the student on the sampled frames under "model_student"; fetched per batch (:173-175,262-263)
+    are the STUDENT's predictions, the student's label loss and the state-matching loss
+    mean_b sum_j (teacher_state - student_state)^2.  The student runs on a second stream next to the teacher."""
+
+    def __init__(self, teacher: HLstmParams, student: HLstmParams, batch_size: int, every_n: int = 10,
+                 num_inputs_to_lstm: int = 20, num_inputs_L1: int = 5, top_k: int = 20, sampling: str = "uniform",
+                 sampling_seed: int = 0):
+        if teacher.cfg != student.cfg or teacher.device != student.device:
+            raise ValueError("teacher and student must share the model configuration and the device")
+        super().__init__(student.cfg, batch_size, student.device, every_n, num_inputs_L1, 0.0, 0.0, 0.0,
+                         sampling=sampling, sampling_seed=sampling_seed)
+        self.teacher, self.student = teacher, student
+        self.t_eng = HLstmEngine(teacher, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=False)
+        self.s_eng = HLstmEngine(student, batch_size, self.student_frames, num_inputs_L1, training=False)
+        self.top_k = top_k
+        self.rows = torch.zeros(batch_size, dtype=torch.float32, device=self.device)             # student CE rows
+        self.state_loss_rows = torch.zeros(batch_size, dtype=torch.float32, device=self.device)  # L_REP rows
+        self.losses = torch.zeros(2, dtype=torch.float32, device=self.device)   # student_label_loss, student_state_loss
+        self.student_stream = (torch.cuda.Stream(device=self.device)
+                               if (overlap_mode() & OVERLAP_STUDENT) and self.device.type == "cuda" else None)
+
+    def step(self, model_input_raw, num_frames, labels=None, u=None):
+        """Returns (student predictions [B,V], top-k idx, top-k values, top-k labels|None).  self.rows holds the
+        student's cross-entropy per video, self.state_loss_rows the squared state distance per video and
+        self.losses their batch means (validate.py's student_label_loss / student_state_loss)."""
+        self._check(model_input_raw, num_frames, labels)
+        t, s, B = self.t_eng, self.s_eng, self.B
+        main, side = torch.cuda.current_stream(), self.student_stream
+        if side is not None:
+            side.wait_stream(main)
+            t.forward_lstm(model_input_raw, None, True, num_frames, num_frames)      # the teacher's classifier is not fetched
+            with torch.cuda.stream(side):
+                idx = self._student_sample(num_frames, u)
+                s.forward(model_input_raw, idx, True, self.nf_student, num_frames)
+            main.wait_stream(side)
+        else:
+            t.forward_lstm(model_input_raw, None, True, num_frames, num_frames)
+            idx = self._student_sample(num_frames, u)
+            s.forward(model_input_raw, idx, True, self.nf_student, num_frames)
+        ops.rep_loss(t.state, s.state, 0.0, self.state_loss_rows, None)
+        ops.reduce_rows(self.state_loss_rows, 1.0 / B, self.losses[1:2])
+        lab = _as_u8(labels) if labels is not None else None
+        if lab is not None:
+            ops.ce_kl_loss(s.pred, None, lab, 1.0, 0.0, self.rows, None, None)
+            ops.reduce_rows(self.rows, 1.0 / B, self.losses[0:1])
+        idx_k, val, tl = ops.topk(s.pred, self.top_k, lab)
+        return s.pred, idx_k, val, tl
+
+
 def evaluation_loop(evaluator, batches, metrics, log=None) -> Dict[str, object]:
     """The `while not coord.should_stop()` loop of eval_finetune.py:240-275 / validate.py:255-290: run every
     batch of `batches` (tuples of `readers.*.batches`) through `evaluator.step`, fold predictions, labels and the
@@ -437,7 +527,7 @@ def evaluation_loop(evaluator, batches, metrics, log=None) -> Dict[str, object]:
     (num_frames = 0, no labels) whose rows are dropped before they reach the metrics."""
     B, dev = evaluator.B, evaluator.device
     metrics.clear()
-    examples, rates = 0, []
+    examples, rates, state_losses = 0, [], []
     for ids, x, y, nf in batches:
         t0 = time.time()
         n = int(x.shape[0])
@@ -450,6 +540,10 @@ def evaluation_loop(evaluator, batches, metrics, log=None) -> Dict[str, object]:
         xd, yd, nd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), nf.to(dev, non_blocking=True)
         pred = evaluator.step(xd, nd, yd)[0]
         info = metrics.accumulate(pred[:n], yd[:n], evaluator.rows[:n])
+        state_rows = getattr(evaluator, "state_loss_rows", None)
+        if state_rows is not None:       # validate.py:262-269: the state-matching loss is logged per batch
+            info = dict(info, student_loss=float(state_rows[:n].mean().item()) if n else 0.0)
+            state_losses.append((info["student_loss"], n))
         dt = max(time.time() - t0, 1e-9)
         examples += n
         rates.append(n / dt)
@@ -459,4 +553,6 @@ def evaluation_loop(evaluator, batches, metrics, log=None) -> Dict[str, object]:
     out = dict(metrics.get())
     out["examples_processed"] = examples
     out["examples_per_second"] = float(sum(rates) / len(rates)) if rates else 0.0
+    if state_losses:
+        out["avg_student_state_loss"] = sum(v * n for v, n in state_losses) / max(sum(n for _, n in state_losses), 1)
     return out

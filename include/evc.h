@@ -70,6 +70,15 @@ int evc_random_frame_index(const float* u, const int* num_frames, int B, int K, 
 /* model_utils.py:23-33 SampleRandomSequence: start=int32(u[b]*float32(max(n-K,0)+1)); min(start+k,n-1). */
 int evc_random_sequence_index(const float* u, const int* num_frames, int B, int K, int* idx, void* stream);
 
+/* Sequence lengths of a randomly sampled student input (BASELINE config #5): both samplers index inside
+ * [0, num_frames), so all K sampled frames are real frames: out[b] = num_frames[b] > 0 ? K : 0 (int64, the
+ * dtype create_model_inference takes, frame_level_models.py:308-309). */
+int evc_sampled_lengths(const int* num_frames, int B, int K, long long* out, void* stream);
+
+/* tf.random_uniform([n], float32) of the two samplers (model_utils.py:25-27,50-51): Philox4x32-10, element i =
+ * lane i%4 of counter offset + i/4 under key `seed`, 23 random mantissa bits -> [0,1) as TF's Uint32ToFloat. */
+int evc_random_uniform(unsigned long long seed, unsigned long long offset, float* out, long long n, void* stream);
+
 /* ---- dense contraction on tcgen05 tensor cores: C[M,N] (=|+=) A[M,K] * B[K,N] (+ bias[N]).
  * a_mn_major=0: A stored [M][lda] (K contiguous); 1: stored [K][lda] (M contiguous).
  * b_mn_major=0: B stored [N][ldb] (K contiguous); 1: stored [K][ldb] (N contiguous).

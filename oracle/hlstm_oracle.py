@@ -141,6 +141,31 @@ def random_sequence_indices(u: np.ndarray, num_frames: np.ndarray, num_samples: 
     return np.minimum(start + off, (n - 1).astype(np.int32))
 
 
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11; the generator behind tf.random_uniform, [TF
+    random_distributions.h PhiloxRandom]) on uint32 arrays: counter [..., 4], key [2] -> [..., 4].
+    Pinned by the Random123 known-answer vectors in tests/test_oracle.py."""
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m0, m1, mask, s32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF), np.uint64(32)
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]
+        c = [((p1 >> s32) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> s32) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_uniform(seed: int, offset: int, n: int) -> np.ndarray:
+    """The U[0,1) float32 stream of evc_random_uniform: element i = lane i%4 of counter (offset + i//4) under
+    the 64-bit key `seed`, converted like TF's Uint32ToFloat (23 mantissa bits -> [1,2) - 1)."""
+    q = (n + 3) // 4
+    ctr = np.uint64(offset) + np.arange(q, dtype=np.uint64)
+    counter = np.stack([ctr & np.uint64(0xFFFFFFFF), ctr >> np.uint64(32), np.zeros(q, np.uint64),
+                        np.zeros(q, np.uint64)], axis=-1)
+    r = philox4x32_10(counter, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(-1)[:n]
+    return ((np.uint32(127 << 23) | (r & np.uint32(0x7FFFFF))).view(np.float32) - np.float32(1.0)).astype(np.float32)
+
+
 def gather_frames(model_input: torch.Tensor, index: np.ndarray) -> torch.Tensor:
     """model_utils.py:34-36,55-58  tf.gather_nd(model_input, stack([batch_index, frame_index], 2))."""
     idx = torch.from_numpy(np.asarray(index, dtype=np.int64))

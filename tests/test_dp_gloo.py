@@ -130,3 +130,51 @@ def test_distributed_evaluation_metrics_world2():
     # and the global GAP equals the oracle's AP over the pooled top-k triplets of all 17 videos
     # (distinct prediction values: no tie order involved)
     assert abs(gap - O.gap(np.concatenate(all_p), np.concatenate(all_a), 5)) < 1e-12
+
+
+def _reader_worker(rank, world, port, tmp, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from efficientvideoclassification_youtube8m_b200 import readers
+    rd = readers.YT8MFrameFeatureReader(num_classes=10, feature_sizes=[8], feature_names=["rgb"])
+    pat = os.path.join(tmp, "train*.tfrecord")
+    res = {}
+    for mode in ("min", "pad"):
+        sizes, ids = [], []
+        for b in readers.get_input_data_batches(rd, pat, 4, num_epochs=2, shuffle=False, rank=rank, world=world,
+                                                uneven=mode, pin_memory=False):
+            # a collective per batch, like the training step / distributed metrics: hangs if the ranks disagree
+            t = torch.tensor([float(len(b[0]))])
+            dist.all_reduce(t)
+            sizes.append((len(b[0]), tuple(b[1].shape[1:]), tuple(b[2].shape[1:])))
+            ids += b[0]
+        res[mode] = (sizes, ids)
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_uneven_shards_keep_ranks_in_step_world2(tmp_path):
+    """shards hold different numbers of videos; ranks must run the same number of steps per epoch
+    ('min': stop with the first rank to run out; 'pad': empty batches until the last rank is done, no video
+    lost) or the per-step collectives hang."""
+    import numpy as np
+    from efficientvideoclassification_youtube8m_b200 import readers
+    rng = np.random.default_rng(2)
+    counts = [9, 2, 5]                      # rank 0 reads shards 0 and 2 (14 videos), rank 1 shard 1 (2 videos)
+    for k, n in enumerate(counts):
+        recs = [readers.make_sequence_example(f"s{k}v{i}", [k], {"rgb": rng.integers(0, 256, (2, 8), dtype=np.uint8)})
+                for i in range(n)]
+        readers.write_tfrecord(str(tmp_path / f"train{k}.tfrecord"), recs)
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_reader_worker, args=(world, _free_port(), str(tmp_path), out), nprocs=world, join=True)
+        got = dict(out)
+    # min: one step per epoch on both ranks (rank 1 has a single batch of 2 videos)
+    assert [s[0] for s in got[0]["min"][0]] == [4, 4] and [s[0] for s in got[1]["min"][0]] == [2, 2]
+    # pad: rank 0 has 4 batches per epoch (4,4,4,2); rank 1 follows with empty batches of the right shapes
+    assert [s[0] for s in got[0]["pad"][0]] == [4, 4, 4, 2] * 2
+    assert [s[0] for s in got[1]["pad"][0]] == [2, 0, 0, 0] * 2
+    assert all(s[1:] == ((300, 8), (10,)) for r in (0, 1) for s in got[r]["pad"][0])
+    ids = got[0]["pad"][1] + got[1]["pad"][1]
+    assert len(ids) == 2 * sum(counts) and len(set(ids)) == sum(counts)      # every video, every epoch

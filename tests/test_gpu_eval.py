@@ -107,6 +107,32 @@ def test_gather_and_random_samplers_bit_exact():
     assert np.array_equal(got, O.gather_frames(torch.from_numpy(x), sidx).numpy())
 
 
+def test_random_uniform_bit_exact_and_empty_video_samplers():
+    """evc_random_uniform == the oracle's Philox4x32-10 stream bit for bit; the samplers with their own draws
+    equal the oracle's index rule on those draws; a video with num_frames = 0 never indexes before its row."""
+    from oracle import hlstm_oracle as O
+    from efficientvideoclassification_youtube8m_b200 import model_utils, ops
+    for n, seed, off in [(1, 0, 0), (7, 5, 0), (4096 + 3, 2 ** 40 + 17, 2 ** 33 + 5)]:
+        u = torch.empty(n, dtype=torch.float32, device="cuda")
+        ops.random_uniform(u, seed, off)
+        assert np.array_equal(u.cpu().numpy(), O.philox_uniform(seed, off, n))
+    rng = np.random.default_rng(4)
+    B, K = 5, 30
+    x = rng.standard_normal((B, 300, 64)).astype(np.float32)
+    nf = np.array([0, 1, 29, 31, 300], dtype=np.int32)
+    x[np.arange(300)[None, :] >= nf[:, None]] = 0.0
+    xd, nfd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda()
+    model_utils.set_random_seed(11)
+    got = model_utils.SampleRandomFrames(xd, nfd.view(-1, 1), K).cpu().numpy()
+    want_idx = O.random_frame_indices(O.philox_uniform(11, 0, B * K).reshape(B, K), nf)
+    assert np.array_equal(got, O.gather_frames(torch.from_numpy(x), want_idx).numpy())
+    got = model_utils.SampleRandomSequence(xd, nfd.view(-1, 1), K).cpu().numpy()      # next counters of the stream
+    u1 = O.philox_uniform(11, (B * K + 3) // 4, B)
+    sidx = np.maximum(O.random_sequence_indices(u1, nf, K), 0)     # n = 0: the reference's -1 is clamped to frame 0
+    assert np.array_equal(got, O.gather_frames(torch.from_numpy(x), sidx).numpy())
+    assert np.all(got[0] == 0)                                       # the empty video samples zero frames
+
+
 def test_l2_normalize_and_zero_frames():
     from oracle import hlstm_oracle as O
     from efficientvideoclassification_youtube8m_b200 import nn_ops

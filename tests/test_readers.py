@@ -230,10 +230,13 @@ def test_get_input_data_batches_epochs_shuffle_and_rank_slices(tmp_path):
     plain = sum((b[0] for b in readers.get_input_data_batches(rd, pat, 4, num_epochs=1, shuffle=False,
                                                                pin_memory=False)), [])
     assert plain == [f"s{k}v{i}" for k in range(5) for i in range(3)]
+    # rank slices order[rank::world]: every shard is read by exactly one rank (the agreement on the epoch length
+    # between ranks is covered with a real process group in tests/test_dp_gloo.py)
     seen = []
     for rank in range(2):
         ids = sum((b[0] for b in readers.get_input_data_batches(rd, pat, 4, num_epochs=1, rank=rank, world=2,
-                                                                 pin_memory=False)), [])
-        assert len(ids) == 6                                                # 2 of the 5 shards each, 1 dropped
+                                                                 pin_memory=False, agree=lambda have: (have, have))),
+                  [])
+        assert len(ids) == (9 if rank == 0 else 6)                          # 3 and 2 of the 5 shards
         seen.append(set(ids))
-    assert not (seen[0] & seen[1])
+    assert not (seen[0] & seen[1]) and len(seen[0] | seen[1]) == 15
