@@ -30,7 +30,9 @@ SIGNATURES = {
     "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
     "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P],
     "evc_lstm_workspace_bytes": [I, I, I],
-    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P, L, P],
+    "evc_lstm_rec_workspace_bytes": [I, I, I],
+    "evc_lstm_seq_fwd_resident": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
+    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P, P, L, P],
     "evc_state_pack": [P, P, P, P, I, I, P, P, P],
     "evc_cast_bf16": [P, L, I, I, P, P],
     "evc_fill_f32": [P, L, F, P],
@@ -44,10 +46,11 @@ SIGNATURES = {
     "evc_colsum_bf16": [P, L, I, L, P, P],
     "evc_sumsq": [P, P, F, L, P, P, P],
     "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P],
+    "evc_batch_metrics": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "evc_topk": [P, I, I, I, P, P, P, P, P],
 }
 _RESTYPES = {"evc_last_error": C.c_char_p, "evc_launch_count": C.c_longlong,
-             "evc_lstm_workspace_bytes": C.c_longlong}
+             "evc_lstm_workspace_bytes": C.c_longlong, "evc_lstm_rec_workspace_bytes": C.c_longlong}
 
 
 class EvcError(RuntimeError):

@@ -259,14 +259,6 @@ static int pick_split(int tiles, int kb_total) {
 extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
   // forward small-row path: S x rows x 4H f32 ; backward: S x rows x H f32
   int sf = (rows <= 1024) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
-  {   // the persistent multi-step kernel may use up to 8 slabs
-    const int tiles = ceil_div(rows, BM) * (4 * H / 256);
-    if (tiles <= num_sms()) {
-      int S = num_sms() / tiles;
-      if (S > 8) S = 8;
-      if (S > sf) sf = S;
-    }
-  }
   const int sb = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
   const long long f = static_cast<long long>(sf) * rows * 4 * H * 4;
   const long long b = static_cast<long long>(sb) * rows * H * 4;
@@ -283,67 +275,12 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: empty problem");
   if (t_begin < 0 || t_end > T || t_begin >= t_end) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: bad step range");
-  const bool whole = (t_begin == 0 && t_end == T);
   if (H % 64 != 0 || Kx % 64 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: H and Kx must be multiples of 64");
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h_all);
   __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
   const long long RH = static_cast<long long>(rows) * H;
   int rc;
-  // EXPERIMENTAL (off unless EVC_PERSISTENT=1): persistent multi-step kernel, every (tile, K split) work item
-  // gets its own resident CTA for all T steps with two grid barriers per step (csrc/evc_rec.cuh).  Measured
-  // on B200 at 256 rows: 32 us/step vs 26 us for split-K GEMM + cell kernel launched with PDL -- the
-  // un-overlapped slab store (8 us) and the two barriers (~3 us each) cost more than the launches they save.
-  {
-    static int persistent = -1;
-    if (persistent < 0) {
-      const char* e = getenv("EVC_PERSISTENT");
-      persistent = e ? atoi(e) : 0;
-    }
-    const int tiles = ceil_div(rows, BM) * (4 * H / 256);
-    if (persistent && whole && workspace != nullptr && T >= 2 && tiles <= num_sms() && H % 64 == 0) {
-      int S = num_sms() / tiles;
-      if (S > 8) S = 8;
-      while (S > 1 && (Kx + H) / BK / S < 8) --S;
-      const long long slab = static_cast<long long>(rows) * 4 * H;
-      if (static_cast<long long>(S) * slab * 4 + 256 > workspace_bytes)
-        return set_error(EVC_ERR_ARG, "lstm_seq_fwd: workspace too small (evc_lstm_workspace_bytes)");
-      unsigned int* bar = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + static_cast<long long>(S) * slab * 4);
-      cudaError_t e = cudaMemsetAsync(bar, 0, 64, stream);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(barrier)");
-      CUtensorMap tx, th, tw;
-      rc = make_tmap_steps(&tx, xb, Kx, rows, T, x_step_stride);
-      if (rc) return rc;
-      rc = make_tmap_steps(&th, hb, H, rows, T + 1, RH);
-      if (rc) return rc;
-      rc = make_tmap_b(&tw, W, 1, 4LL * H, 4 * H, Kx + H, 256, 1);
-      if (rc) return rc;
-      RecArgs a = {};
-      a.rows = rows; a.H = H; a.T = T;
-      a.tiles_m = ceil_div(rows, BM); a.tiles_n = 4 * H / 256; a.S = S;
-      a.kb_x = Kx / BK; a.kb_h = H / BK;
-      a.bias = bias; a.seq_len = seq_len;
-      a.c_all = c_all; a.h_all = hb; a.gates_all = gb;
-      a.slabs = static_cast<float*>(workspace);
-      a.barrier = bar;
-      rc = opt_in_smem(reinterpret_cast<const void*>(lstm_rec_fwd_kernel), GemmCfg<256>::SMEM_BYTES);
-      if (rc) return rc;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(tiles * S);
-      cfg.blockDim = dim3(GEMM_THREADS);
-      cfg.dynamicSmemBytes = GemmCfg<256>::SMEM_BYTES;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, lstm_rec_fwd_kernel, tx, th, tw, a);
-      count_launch();
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(lstm_rec_fwd_kernel)");
-      return check_launch("lstm_rec_fwd_kernel");
-    }
-  }
   if (rows <= 1024 && workspace != nullptr) {
     // Small-row steps (RNN_L2, student): one 128x256 tile per CTA would serialise the whole K on a few
     // SMs.  Split K over the SMs into f32 partial slabs, then one full-occupancy cell kernel sums
@@ -399,6 +336,110 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
   return EVC_OK;
 }
 
+// ------------------------------------------------------------------ resident-weights persistent recurrence
+// (csrc/evc_rec.cuh).  Plan: G row groups x H/16 unit slices of co-resident CTAs.
+struct RecPlan {
+  int tiles_m, n_slices, groups, tiles_per_cta;
+  long long zx_bytes, wp_bytes, flag_bytes;
+  bool ok;
+};
+static RecPlan rec_plan(int rows, int H, int T) {
+  RecPlan p = {};
+  p.ok = false;
+  if (rows <= 0 || T <= 0 || H % BK != 0) return p;
+  p.tiles_m = ceil_div(rows, BM);
+  p.n_slices = H / REC_UNITS;
+  if (p.n_slices > num_sms() || rec_smem_bytes(H) > 227 * 1024) return p;
+  p.groups = num_sms() / p.n_slices;
+  if (p.groups > p.tiles_m) p.groups = p.tiles_m;
+  p.tiles_per_cta = ceil_div(p.tiles_m, p.groups);
+  if (p.tiles_per_cta > REC_MAX_TILES) return p;
+  p.groups = ceil_div(p.tiles_m, p.tiles_per_cta);          // no empty groups
+  p.zx_bytes = ((static_cast<long long>(T) * rows * 4 * H * 4 + 1023) / 1024) * 1024;
+  p.wp_bytes = static_cast<long long>(H) * 4 * H * 2;
+  p.flag_bytes = ((static_cast<long long>(T) * p.tiles_m * 4 + 255) / 256) * 256;
+  p.ok = true;
+  return p;
+}
+
+extern "C" long long evc_lstm_rec_workspace_bytes(int rows, int H, int T) {
+  const RecPlan p = rec_plan(rows, H, T);
+  return p.ok ? p.zx_bytes + p.wp_bytes + p.flag_bytes : 0;
+}
+
+extern "C" int evc_lstm_seq_fwd_resident(const void* x, long long x_step_stride, int Kx, const void* W,
+                                         const float* bias, int rows, int H, int T, const int* seq_len, void* h_all,
+                                         float* c_all, void* gates_all, void* workspace, long long workspace_bytes,
+                                         void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const RecPlan p = rec_plan(rows, H, T);
+  if (!p.ok) return set_error(EVC_ERR_UNSUPPORTED, "lstm_seq_fwd_resident: shape not eligible (evc_lstm_rec_workspace_bytes == 0)");
+  if (Kx % BK != 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd_resident: Kx must be a multiple of 64");
+  if (x_step_stride != static_cast<long long>(rows) * Kx)
+    return set_error(EVC_ERR_ARG, "lstm_seq_fwd_resident: the input steps must be contiguous ([T*rows, Kx])");
+  if (workspace == nullptr || workspace_bytes < p.zx_bytes + p.wp_bytes + p.flag_bytes)
+    return set_error(EVC_ERR_ARG, "lstm_seq_fwd_resident: workspace too small (evc_lstm_rec_workspace_bytes)");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+    return set_error(EVC_ERR_ARG, "lstm_seq_fwd_resident: workspace must be 1024-byte aligned");
+  char* ws = static_cast<char*>(workspace);
+  float* zx = reinterpret_cast<float*>(ws);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + p.zx_bytes);
+  unsigned int* ready = reinterpret_cast<unsigned int*>(ws + p.zx_bytes + p.wp_bytes);
+  const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(W);
+  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h_all);
+  // 1. the slice layout of the recurrent rows of the kernel
+  {
+    const long long n = static_cast<long long>(p.n_slices) * H * 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_pack_wh_kernel, wb + static_cast<long long>(Kx) * 4 * H, H, wp);
+    count_launch();
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(lstm_pack_wh_kernel)");
+  }
+  // 2. the input projection of all steps: Zx = X Wx + bias  ([T*rows, Kx] x [Kx, 4H], f32)
+  int rc = gemm_store(x, 0, Kx, W, 1, 4LL * H, T * rows, 4 * H, Kx, zx, 0, 4LL * H, bias, 1, 0, stream);
+  if (rc) return rc;
+  // 3. the recurrence
+  cudaError_t e = cudaMemsetAsync(ready, 0, static_cast<size_t>(p.flag_bytes), stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(ready flags)");
+  CUtensorMap th, tw;
+  rc = make_tmap_steps(&th, hb, H, rows, T + 1, static_cast<long long>(rows) * H);
+  if (rc) return rc;
+  rc = make_tmap(&tw, wp, REC_BN, static_cast<uint64_t>(p.n_slices) * H, REC_BN, REC_BN, BK);
+  if (rc) return rc;
+  RecArgs a = {};
+  a.rows = rows; a.H = H; a.T = T;
+  a.tiles_m = p.tiles_m; a.groups = p.groups; a.tiles_per_cta = p.tiles_per_cta;
+  a.zx = zx; a.seq_len = seq_len; a.c_all = c_all; a.h_all = hb;
+  a.gates_all = static_cast<__nv_bfloat16*>(gates_all);
+  a.ready = ready;
+  const size_t smem = rec_smem_bytes(H);
+  // (the opt-in is cached per kernel and device: ask for the maximum once, launches use what their H needs)
+  rc = opt_in_smem(reinterpret_cast<const void*>(lstm_rec_resident_fwd_kernel), 227 * 1024);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(p.groups * p.n_slices));
+  cfg.blockDim = dim3(REC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, lstm_rec_resident_fwd_kernel, th, tw, a);
+  count_launch();
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(lstm_rec_resident_fwd_kernel)");
+  return check_launch("lstm_rec_resident_fwd_kernel");
+}
+
 extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
                                 int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
                                 void* gates_all, void* workspace, long long workspace_bytes, void* stream_) {
@@ -410,10 +451,13 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
 extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len,
                                 const void* gates_all, const float* c_all, const float* dh_ext_all,
                                 const float* dh_final, long long ld_dh_final, const float* dc_final,
-                                long long ld_dc_final, float* dh_pass, float* dc, void* dz_all, void* workspace,
-                                long long workspace_bytes, void* stream_) {
+                                long long ld_dc_final, float* dh_pass, float* dc, void* dz_all, float* dbias,
+                                void* workspace, long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: empty problem");
+  if (dbias != nullptr && workspace == nullptr)
+    return set_error(EVC_ERR_UNSUPPORTED, "lstm_seq_bwd: the bias gradient is fused into the cell kernel of the "
+                                          "workspace path (use evc_colsum_bf16 over dz with the fused-epilogue path)");
   if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: H must be a multiple of 128");
   const __nv_bfloat16* gb = static_cast<const __nv_bfloat16*>(gates_all);
   __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(dz_all);
@@ -428,6 +472,10 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     const int want = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
     if (static_cast<long long>(want) * RH * 4 > workspace_bytes)
       return set_error(EVC_ERR_ARG, "lstm_seq_bwd: workspace too small (evc_lstm_workspace_bytes)");
+    if (dbias != nullptr) {
+      cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * 4 * H, stream);
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(dbias)");
+    }
     for (int t = T - 1; t >= 0; --t) {
       const bool last = (t == T - 1);
       int splits = 0;
@@ -439,7 +487,7 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
       int rc = launch_lstm_cell_bwd(part, splits, RH, gb + t * RH * 4, (t == 0) ? nullptr : c_all + t * RH,
                                     dh_ext_all ? dh_ext_all + t * RH : nullptr, H, last ? dh_final : dh_pass,
                                     last ? ld_dh_final : H, last ? dc_final : dc, last ? ld_dc_final : H, seq_len, t,
-                                    rows, H, zb + t * RH * 4, dc, dh_pass, stream);
+                                    rows, H, zb + t * RH * 4, dc, dh_pass, dbias, stream);
       if (rc) return rc;
     }
     return EVC_OK;

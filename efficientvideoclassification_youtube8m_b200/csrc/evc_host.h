@@ -22,5 +22,5 @@ int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, cons
 int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, const void* gates, const float* c_prev,
                          const float* dh_ext, long long ld_dh_ext, const float* dh_pass_in, long long ld_dh_pass_in,
                          const float* dc_in, long long ld_dc_in, const int* seq_len, int t, int rows, int H,
-                         void* dz_out, float* dc_out, float* dh_pass_out, cudaStream_t stream);
+                         void* dz_out, float* dc_out, float* dh_pass_out, float* dbias, cudaStream_t stream);
 }  // namespace evc

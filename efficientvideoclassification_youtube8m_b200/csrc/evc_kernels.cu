@@ -336,77 +336,106 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, lo
 }
 
 // BasicLSTMCell backward at step t: dh = sum_s dh_part[s] (= dz_{t+1} Wh^T) + dh_ext + pass-through;
-// gate gradients dz_t (bf16), carried dc, masked pass-through.  Thread = (row, 4 units).
-__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_stride,
-                                     const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_prev,
-                                     const float* __restrict__ dh_ext, long long ld_dh_ext,
-                                     const float* __restrict__ dh_pass_in, long long ld_dh_pass_in,
-                                     const float* __restrict__ dc_in, long long ld_dc_in,
-                                     const int* __restrict__ seq_len, int t, int rows, int H,
-                                     __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dc_out,
-                                     float* __restrict__ dh_pass_out) {
+// gate gradients dz_t (bf16), carried dc, masked pass-through, and the bias gradient db += column sums of dz_t
+// (nullable; fused here so that dz is not read a second time by a column-sum pass).
+// Block = 8 rows x 32 unit-quads (128 units of one column block); blockIdx.x = column block, blockIdx.y strides
+// over groups of 8 rows, so a thread keeps the column sums of its 16 gate columns in registers over all its rows
+// and the block issues 512 atomics at the end.
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_stride,
+                     const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_prev,
+                     const float* __restrict__ dh_ext, long long ld_dh_ext,
+                     const float* __restrict__ dh_pass_in, long long ld_dh_pass_in,
+                     const float* __restrict__ dc_in, long long ld_dc_in,
+                     const int* __restrict__ seq_len, int t, int rows, int H,
+                     __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dc_out,
+                     float* __restrict__ dh_pass_out, float* __restrict__ dbias) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL (see evc_ptx.cuh)
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int hq = H >> 2;
-  if (idx >= static_cast<long long>(rows) * hq) return;
-  const int r = static_cast<int>(idx / hq);
-  const int u = static_cast<int>(idx % hq) * 4;
-  const long long off = static_cast<long long>(r) * H + u;
-  const int len = seq_len[r];
-  const bool live = t < len;
-  float dh[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s = 0; s < S; ++s) {
-    const float4 a = *reinterpret_cast<const float4*>(dh_part + s * part_stride + off);
-    dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
-  }
-  if (dh_ext != nullptr) {
-    const float4 a = *reinterpret_cast<const float4*>(dh_ext + static_cast<long long>(r) * ld_dh_ext + u);
-    dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
-  }
-  if (t + 1 >= len && dh_pass_in != nullptr) {   // row was masked at step t+1 (or t is the last step)
-    const float4 a = *reinterpret_cast<const float4*>(dh_pass_in + static_cast<long long>(r) * ld_dh_pass_in + u);
-    dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
-  }
-  if (dc_in != nullptr) {
-    const float4 a = *reinterpret_cast<const float4*>(dc_in + static_cast<long long>(r) * ld_dc_in + u);
-    dc[0] = a.x; dc[1] = a.y; dc[2] = a.z; dc[3] = a.w;
-  }
-  __nv_bfloat16* zp = dz_out + static_cast<long long>(r) * 4 * H + u;
-  if (!live) {
+  __shared__ float red[8][4][132];               // [row lane][gate][128 units + pad]
+  const int ql = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int u = (blockIdx.x * 32 + ql) * 4;      // first of this thread's 4 units
+  float bsum[4][4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
-    *reinterpret_cast<float4*>(dc_out + off) = make_float4(dc[0], dc[1], dc[2], dc[3]);
-    *reinterpret_cast<float4*>(dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
-    return;
-  }
-  const __nv_bfloat16* gp = gates + static_cast<long long>(r) * 4 * H + u;
-  float gi[4], gj[4], gf[4], go[4], cp[4] = {0.f, 0.f, 0.f, 0.f};
-  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 0 * H), gi);
-  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 1 * H), gj);
-  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 2 * H), gf);
-  unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 3 * H), go);
-  if (c_prev != nullptr) {
-    const float4 a = *reinterpret_cast<const float4*>(c_prev + off);
-    cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w;
-  }
-  float di[4], dj[4], df[4], dq[4], dco[4];
+  for (int g = 0; g < 4; ++g)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float cn = cp[k] * gf[k] + gi[k] * gj[k];
-    const float tc = tanh_(cn);
-    const float dcn = dc[k] + dh[k] * go[k] * (1.f - tc * tc);
-    di[k] = dcn * gj[k] * gi[k] * (1.f - gi[k]);
-    dj[k] = dcn * gi[k] * (1.f - gj[k] * gj[k]);
-    df[k] = dcn * cp[k] * gf[k] * (1.f - gf[k]);
-    dq[k] = dh[k] * tc * go[k] * (1.f - go[k]);
-    dco[k] = dcn * gf[k];
+    for (int k = 0; k < 4; ++k) bsum[g][k] = 0.f;
+  for (int r = blockIdx.y * 8 + rl; r < rows; r += gridDim.y * 8) {
+    const long long off = static_cast<long long>(r) * H + u;
+    const int len = seq_len[r];
+    const bool live = t < len;
+    float dh[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < S; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(dh_part + s * part_stride + off);
+      dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
+    }
+    if (dh_ext != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(dh_ext + static_cast<long long>(r) * ld_dh_ext + u);
+      dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
+    }
+    if (t + 1 >= len && dh_pass_in != nullptr) {   // row was masked at step t+1 (or t is the last step)
+      const float4 a = *reinterpret_cast<const float4*>(dh_pass_in + static_cast<long long>(r) * ld_dh_pass_in + u);
+      dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w;
+    }
+    if (dc_in != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(dc_in + static_cast<long long>(r) * ld_dc_in + u);
+      dc[0] = a.x; dc[1] = a.y; dc[2] = a.z; dc[3] = a.w;
+    }
+    __nv_bfloat16* zp = dz_out + static_cast<long long>(r) * 4 * H + u;
+    if (!live) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
+      *reinterpret_cast<float4*>(dc_out + off) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+      *reinterpret_cast<float4*>(dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+      continue;
+    }
+    const __nv_bfloat16* gp = gates + static_cast<long long>(r) * 4 * H + u;
+    float gi[4], gj[4], gf[4], go[4], cp[4] = {0.f, 0.f, 0.f, 0.f};
+    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 0 * H), gi);
+    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 1 * H), gj);
+    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 2 * H), gf);
+    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 3 * H), go);
+    if (c_prev != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(c_prev + off);
+      cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w;
+    }
+    float dz[4][4], dco[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float cn = cp[k] * gf[k] + gi[k] * gj[k];
+      const float tc = tanh_(cn);
+      const float dcn = dc[k] + dh[k] * go[k] * (1.f - tc * tc);
+      dz[0][k] = dcn * gj[k] * gi[k] * (1.f - gi[k]);
+      dz[1][k] = dcn * gi[k] * (1.f - gj[k] * gj[k]);
+      dz[2][k] = dcn * cp[k] * gf[k] * (1.f - gf[k]);
+      dz[3][k] = dh[k] * tc * go[k] * (1.f - go[k]);
+      dco[k] = dcn * gf[k];
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint2 packed = pack4_bf16(dz[g][0], dz[g][1], dz[g][2], dz[g][3]);
+      *reinterpret_cast<uint2*>(zp + g * H) = packed;
+      // the bias gradient sums the values the weight-gradient GEMMs see: the bf16-rounded dz
+      float q[4];
+      unpack4_bf16(packed, q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bsum[g][k] += q[k];
+    }
+    *reinterpret_cast<float4*>(dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
   }
-  *reinterpret_cast<uint2*>(zp + 0 * H) = pack4_bf16(di[0], di[1], di[2], di[3]);
-  *reinterpret_cast<uint2*>(zp + 1 * H) = pack4_bf16(dj[0], dj[1], dj[2], dj[3]);
-  *reinterpret_cast<uint2*>(zp + 2 * H) = pack4_bf16(df[0], df[1], df[2], df[3]);
-  *reinterpret_cast<uint2*>(zp + 3 * H) = pack4_bf16(dq[0], dq[1], dq[2], dq[3]);
-  *reinterpret_cast<float4*>(dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+  if (dbias == nullptr) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[rl][g][ql * 4 + k] = bsum[g][k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int g = i >> 7, c = i & 127;
+    float acc = 0.f;
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) acc += red[r8][g][c];
+    if (acc != 0.f) atomicAdd(dbias + g * H + blockIdx.x * 128 + c, acc);
+  }
 }
 
 // f32 [R,C] -> bf16 [R,ld] (columns C..ld-1 zero): bf16 operand copies of weights / activations
@@ -752,6 +781,110 @@ __global__ void topk_kernel(const float* __restrict__ P, int V, int k, const uin
   }
 }
 
+// eval_util.py:34-59 calculate_precision_at_equal_recall_rate, per video, without a sort: a labelled class c is
+// among the video's top-num_labels predictions iff fewer than num_labels classes rank before it under the top-k
+// kernel's order (value descending, lower class index first).  rows[b] = |{labelled c in the top-n with p > 0}| / n
+// (0 for a video without labels), npos[b] = n, class_pos[c] += 1 for every labelled class (nullable; the
+// per-class positives of eval_util.py:114).  One block per video, one warp per labelled class.
+__global__ void video_perr_kernel(const float* __restrict__ P, const uint8_t* __restrict__ labels, int V,
+                                  float* __restrict__ perr_rows, int* __restrict__ npos_rows,
+                                  int* __restrict__ class_pos) {
+  PDL_PROLOGUE();
+  extern __shared__ int lab_list[];           // labelled classes of this video (<= V entries)
+  __shared__ int s_count, s_hits;
+  const int b = blockIdx.x;
+  const float* p = P + static_cast<long long>(b) * V;
+  const uint8_t* y = labels + static_cast<long long>(b) * V;
+  if (threadIdx.x == 0) { s_count = 0; s_hits = 0; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < V; c += blockDim.x)
+    if (y[c]) {
+      lab_list[atomicAdd(&s_count, 1)] = c;
+      if (class_pos) atomicAdd(class_pos + c, 1);
+    }
+  __syncthreads();
+  const int n = s_count;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int e = warp; e < n; e += nwarps) {
+    const int c = lab_list[e];
+    const float pc = p[c];
+    int before = 0;
+    for (int j = lane; j < V; j += 32) {
+      const float pj = p[j];
+      before += (pj > pc || (pj == pc && j < c)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0 && before < n && pc > 0.f) atomicAdd(&s_hits, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    perr_rows[b] = n > 0 ? static_cast<float>(s_hits) / static_cast<float>(n) : 0.f;
+    npos_rows[b] = n;
+  }
+}
+
+// eval_util.py:61-79 calculate_gap on the batch's pooled top-k triplets (average_precision_calculator.py:166-232:
+// sort by prediction descending, AP = sum over hits of precision-at-rank / numpos) by rank counting instead of a
+// sort: for a hit i, rank = 1 + #{j before i}, positives so far = 1 + #{hits j before i}, "before" = larger
+// prediction, ties by (class, video) ascending -- the order the reference's regrouping by class feeds its sort.
+// acc[0] += sum of precisions (double).  Thread = one triplet; only hits loop.
+__global__ void gap_rank_kernel(const int* __restrict__ idx, const float* __restrict__ val,
+                                const uint8_t* __restrict__ lab, int n, int k, double* __restrict__ acc) {
+  PDL_PROLOGUE();
+  __shared__ float sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (i < n && lab[i]) {
+    const float vi = val[i];
+    const int ci = idx[i], bi = i / k;
+    int before = 0, hits_before = 0;
+    for (int j = 0; j < n; ++j) {
+      const float vj = val[j];
+      bool first = vj > vi;
+      if (vj == vi) {
+        const int cj = idx[j], bj = j / k;
+        first = cj < ci || (cj == ci && bj < bi);
+      }
+      before += first ? 1 : 0;
+      hits_before += (first && lab[j]) ? 1 : 0;
+    }
+    contrib = static_cast<float>(hits_before + 1) / static_cast<float>(before + 1);
+  }
+  contrib = block_sum(contrib, sh);
+  if (threadIdx.x == 0 && contrib != 0.f) atomicAdd(acc, static_cast<double>(contrib));
+}
+
+// out[0] = mean hit@1 (label of every video's top prediction, eval_util.py:17-31), out[1] = mean PERR,
+// out[2] = GAP = acc / sum(npos) (0 without positives); sums[0..3] += (n videos, hit sum, perr sum, loss sum)
+// when non-null (the epoch accumulators of EvaluationMetrics).  Single block.
+__global__ void batch_metrics_finalize_kernel(const uint8_t* __restrict__ lab, int B, int k,
+                                              const float* __restrict__ perr_rows, const int* __restrict__ npos_rows,
+                                              const float* __restrict__ loss_rows, double* __restrict__ acc,
+                                              float* __restrict__ out, double* __restrict__ sums) {
+  PDL_PROLOGUE();
+  __shared__ float sh[32];
+  float hit = 0.f, perr = 0.f, npos = 0.f, loss = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    hit += lab[static_cast<long long>(b) * k] ? 1.f : 0.f;
+    perr += perr_rows[b];
+    npos += static_cast<float>(npos_rows[b]);
+    if (loss_rows) loss += loss_rows[b];
+  }
+  hit = block_sum(hit, sh);
+  perr = block_sum(perr, sh);
+  npos = block_sum(npos, sh);
+  loss = block_sum(loss, sh);
+  if (threadIdx.x == 0) {
+    out[0] = B > 0 ? hit / B : 0.f;
+    out[1] = B > 0 ? perr / B : 0.f;
+    out[2] = npos > 0.f ? static_cast<float>(acc[0] / static_cast<double>(npos)) : 0.f;
+    out[3] = B > 0 ? loss / B : 0.f;
+    acc[0] = 0.0;                                   // ready for the next batch
+    if (sums) { sums[0] += B; sums[1] += hit; sums[2] += perr; sums[3] += loss; }
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   PDL_PROLOGUE();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -792,10 +925,14 @@ int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, cons
 int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, const void* gates, const float* c_prev,
                          const float* dh_ext, long long ld_dh_ext, const float* dh_pass_in, long long ld_dh_pass_in,
                          const float* dc_in, long long ld_dc_in, const int* seq_len, int t, int rows, int H,
-                         void* dz_out, float* dc_out, float* dh_pass_out, cudaStream_t stream) {
-  const long long n = static_cast<long long>(rows) * (H / 4);
+                         void* dz_out, float* dc_out, float* dh_pass_out, float* dbias, cudaStream_t stream) {
+  if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_cell_bwd: H must be a multiple of 128");
+  const int col_blocks = H / 128;
+  int row_groups = (rows + 7) / 8;
+  const int cap = (num_sms() * 4 + col_blocks - 1) / col_blocks;     // ~4 resident blocks per SM in one wave
+  if (row_groups > cap) row_groups = cap;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
+  cfg.gridDim = dim3(static_cast<unsigned>(col_blocks), static_cast<unsigned>(row_groups));
   cfg.blockDim = dim3(256);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -805,7 +942,7 @@ int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, con
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, dh_part, S, part_stride, static_cast<const __nv_bfloat16*>(gates),
                      c_prev, dh_ext, ld_dh_ext, dh_pass_in, ld_dh_pass_in, dc_in, ld_dc_in, seq_len, t, rows, H,
-                     static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out);
+                     static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out, dbias);
   count_launch();
   return check_launch("lstm_cell_bwd");
 }
@@ -1011,6 +1148,26 @@ extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long 
       static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow);
   count_launch();
   return check_launch("clip_adam");
+}
+
+extern "C" int evc_batch_metrics(const float* P, const unsigned char* labels, int B, int V, int k, const int* idx,
+                                 const float* val, const unsigned char* lab, const float* loss_rows,
+                                 float* perr_rows, int* npos_rows, int* class_pos, double* acc, float* out,
+                                 double* sums, void* stream) {
+  if (B <= 0) return EVC_OK;
+  if (k <= 0) return set_error(EVC_ERR_ARG, "batch_metrics: k must be a positive integer");
+  if (!P || !labels || !idx || !val || !lab || !perr_rows || !npos_rows || !acc || !out)
+    return set_error(EVC_ERR_ARG, "batch_metrics: null argument");
+  pdl_launch(video_perr_kernel, dim3(B), dim3(256), static_cast<size_t>(V) * sizeof(int), EVC_STREAM(stream), P, labels,
+             V, perr_rows, npos_rows, class_pos);
+  count_launch();
+  const int n = B * k;
+  pdl_launch(gap_rank_kernel, dim3((n + 127) / 128), dim3(128), 0, EVC_STREAM(stream), idx, val, lab, n, k, acc);
+  count_launch();
+  pdl_launch(batch_metrics_finalize_kernel, dim3(1), dim3(256), 0, EVC_STREAM(stream), lab, B, k, perr_rows, npos_rows,
+             loss_rows, acc, out, sums);
+  count_launch();
+  return check_launch("batch_metrics");
 }
 
 extern "C" int evc_topk(const float* P, int B, int V, int k, const unsigned char* labels, int* idx_out,

@@ -38,6 +38,17 @@ BF16 = torch.bfloat16
 OVERLAP_STUDENT, OVERLAP_CELLS, OVERLAP_WGRAD, OVERLAP_OPTIMIZER, OVERLAP_CELLS_L2 = 1, 2, 4, 8, 16
 
 
+# The resident-weights persistent recurrence (csrc/evc_rec.cuh) needs all its CTAs co-resident; two such grids
+# launched on different streams could each hold part of the SMs and wait for the rest forever.  Every launch
+# therefore waits for the previous one of the process (any stream) through this event.
+_REC_TOKEN = {}
+
+
+def resident_mode() -> bool:
+    """EVC_RESIDENT=0 switches the persistent recurrence off (per-step split-K GEMM + cell kernel instead)."""
+    return os.environ.get("EVC_RESIDENT", "1") != "0"
+
+
 def overlap_mode() -> int:
     """Default 7.  Bit 8 measured no gain on the joint step and -4 % on the cfg #4 fine-tune step (the
     optimizer's HBM traffic slows the power-capped GEMMs it runs next to); bit 16 = the same interleaving
@@ -91,6 +102,14 @@ class HLstmEngine:
         self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
         self.workspace2 = (torch.empty(ops.lstm_workspace_bytes(B, H, H), dtype=torch.uint8, device=dev)
                            if self.overlap & OVERLAP_CELLS_L2 else None)
+        # scratch of the resident-weights persistent recurrence (hoisted input projection Zx, slice layout of Wh,
+        # step flags) for the cells whose row count is eligible: RNN_L2 always, RNN_L1 up to ~2048 rows
+        rec = max(ops.lstm_rec_workspace_bytes(R1, H, ell), ops.lstm_rec_workspace_bytes(B, H, C)) if resident_mode() else 0
+        self.rec_ws = None
+        if rec:
+            raw = torch.empty(rec + 1024, dtype=torch.uint8, device=dev)
+            skip = (-raw.data_ptr()) % 1024
+            self.rec_ws = raw[skip:skip + rec]
         if training:
             self.lddg, self.ldde = ops.pad8(self.ldg, 64), ops.pad8(self.lde, 64)
             self.dG = torch.zeros(B, self.lddg, dtype=BF16, device=dev)
@@ -119,9 +138,37 @@ class HLstmEngine:
     def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len, t_begin=0, t_end=None,
                   cuda_stream=None, workspace=None):
         p = self.p
+        if (t_begin == 0 and t_end is None and cuda_stream is None and self._resident_ok(layer)
+                and x_stride == layer.rows * Kx):
+            dev, cur = p.device, torch.cuda.current_stream()
+            prev = _REC_TOKEN.get(dev)
+            if prev is not None:
+                cur.wait_event(prev)
+            ops.lstm_seq_fwd_resident(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
+                                      layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates,
+                                      self.rec_ws)
+            ev = prev if prev is not None else torch.cuda.Event()
+            ev.record(cur)
+            _REC_TOKEN[dev] = ev
+            return
         ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[p.kernel(level, cell)], p.w[p.bias(level, cell)],
                          layer.rows, layer.H, layer.T, seq_len, layer.h_all, layer.c_all, layer.gates,
                          self.workspace if workspace is None else workspace, t_begin, t_end, cuda_stream)
+
+    def _resident_ok(self, layer: _Layer) -> bool:
+        """Use the persistent resident-weights kernel where it is measured faster than the per-step path
+        (profiles/r02_resident_recurrence.md): one 128-row tile per CTA (rows <= 256 at H = 1024) and enough steps
+        to amortise the one-off slice load + hoisted projection; EVC_RESIDENT=2 forces it wherever it is eligible."""
+        if self.rec_ws is None:
+            return False
+        need = ops.lstm_rec_workspace_bytes(layer.rows, layer.H, layer.T)
+        if not 0 < need <= self.rec_ws.numel():
+            return False
+        if os.environ.get("EVC_RESIDENT", "1") == "2":
+            return True
+        slices = layer.H // 16
+        groups = max(1, min(148 // slices, (layer.rows + 127) // 128))
+        return (layer.rows + 127) // 128 <= groups and layer.T >= 8
 
     def _cells_interleaved(self, a: _Layer, b: _Layer, x, x_stride, Kx, level, seq_len, workspace_b=None):
         """MultiRNNCell wavefront: cell 1 step t (side stream) next to cell 0 step t+1 (current stream)."""
@@ -161,7 +208,7 @@ class HLstmEngine:
             ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x)
         ops.lstm_lengths(num_frames, C, ell, self.len_l1, self.len_l2)
         a, b = self.l1
-        if (self.overlap & OVERLAP_CELLS) and R1 > 1024:
+        if (self.overlap & OVERLAP_CELLS) and R1 > 1024 and not self._resident_ok(a):
             # MultiRNNCell wavefront: cell 1 step t next to cell 0 step t+1 (fused-epilogue steps only: the
             # split-K path of the small-row steps shares one scratch buffer)
             self._cells_interleaved(a, b, self.x, R1 * D, D, 0, self.len_l1)
@@ -170,7 +217,7 @@ class HLstmEngine:
             self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1)
         ops.state_pack(a.c_all[ell], a.h_all[ell], b.c_all[ell], b.h_all[ell], R1, H, out_bf16=self.l2_in)
         a2, b2 = self.l2
-        if self.workspace2 is not None and B <= 1024:
+        if self.workspace2 is not None and B <= 1024 and not self._resident_ok(a2):
             self._cells_interleaved(a2, b2, self.l2_in, B * S, S, 1, self.len_l2, self.workspace2)
         else:
             self._cell_fwd(a2, self.l2_in, B * S, S, 1, 0, self.len_l2)
@@ -204,21 +251,19 @@ class HLstmEngine:
         p = self.p
         H = layer.H
         ld = dfinal.stride(0)
+        # (the bias gradient -- column sums of dz -- is accumulated by the cell kernel while it writes dz)
         ops.lstm_seq_bwd(p.shadow[p.kernel(level, cell)], Kx, layer.rows, H, layer.T, seq_len, layer.gates,
                          layer.c_all, dh_ext, dfinal[:, col + H:], ld, dfinal[:, col:], ld,
-                         scratch[0], scratch[1], layer.dz, self.workspace)
+                         scratch[0], scratch[1], layer.dz, self.workspace, dbias=p.g[p.bias(level, cell)])
 
     def _cell_wgrad(self, layer: _Layer, level, cell, x2d, Kx):
-        """dW = [x | h_prev]^T dz over all steps and rows; db = column sums of dz."""
+        """dW = [x | h_prev]^T dz over all steps and rows (db comes from the backward recurrence, _cell_bwd)."""
         p = self.p
         H, R = layer.H, layer.T * layer.rows
         dz = layer.dz.view(R, 4 * H)
         gW = p.g[p.kernel(level, cell)]
         ops.gemm(x2d, dz, Kx, 4 * H, R, gW[:Kx], a_mn=True, b_mn=True, lda=Kx, ldc=4 * H)
         ops.gemm(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], a_mn=True, b_mn=True, lda=H, ldc=4 * H)
-        gb = p.g[p.bias(level, cell)]
-        ops.fill_f32(gb, 0.0)
-        ops.colsum_bf16(dz, R, 4 * H, 4 * H, gb)
 
     def _cell_dx(self, layer: _Layer, level, cell, Kx, out):
         """d input sequence = dz @ Wx^T  (Wx = first Kx rows of the kernel)."""

@@ -96,18 +96,39 @@ def calculate_gap(predictions, actuals, top_k=20):
     return gap_calculator.peek_ap_at_n()
 
 
+def _loss_rows(loss, n, device):
+    """The reference passes the batch-mean label loss (a scalar, validate.py:262-266); this package's evaluators
+    keep the per-video cross-entropy rows on the device.  Either becomes an f32 device vector of n rows."""
+    if torch.is_tensor(loss) and loss.is_cuda and loss.numel() == n and loss.dtype == torch.float32:
+        return loss.reshape(n).contiguous()
+    v = np.asarray(loss.detach().cpu().numpy() if torch.is_tensor(loss) else loss, dtype=np.float64).reshape(-1)
+    v = np.full(n, float(v.mean()) if v.size else 0.0) if v.size != n else v
+    return torch.as_tensor(v.astype(np.float32), device=device)
+
+
 def batch_stats(predictions, labels, loss, top_k):
-    """What one batch contributes to EvaluationMetrics, as small host arrays: the per-video top-k triplets
-    (selected on the GPU), the positives per class, and the hit@1 / PERR / loss sums."""
+    """What one batch contributes to EvaluationMetrics, as small host arrays: the per-video top-k triplets, the
+    positives per class, and the hit@1 / PERR / loss sums -- all computed on the GPU (one top-k launch + the
+    fused metrics kernels of evc_batch_metrics) and brought to the host in ONE copy."""
     p, a = _dev(predictions, labels)
-    batch_size = int(a.shape[0])
-    idx, val, lab = top_k_device(p, a, top_k)
-    mean_loss = float(np.mean(loss.cpu().numpy() if torch.is_tensor(loss) else loss))
-    return {"n": batch_size, "idx": idx, "val": val, "lab": lab,
-            "num_positives": a.sum(dim=0).cpu().numpy().astype(np.float64),
-            "hit_sum": calculate_hit_at_one(p, a) * batch_size,
-            "perr_sum": calculate_precision_at_equal_recall_rate(p, a) * batch_size,
-            "loss_sum": mean_loss * batch_size}
+    n, V = int(a.shape[0]), int(a.shape[1])
+    k = min(top_k, V)
+    if n == 0:
+        z = np.zeros((0, k))
+        return {"n": 0, "idx": z.astype(np.int32), "val": z.astype(np.float32), "lab": z.astype(np.uint8),
+                "num_positives": np.zeros(V), "hit_sum": 0.0, "perr_sum": 0.0, "loss_sum": 0.0}
+    bm = ops.BatchMetrics(n, V, k, p.device, accumulate=True)
+    out, idx, val, lab = bm.run(p, a, _loss_rows(loss, n, p.device))
+    packed = torch.cat([idx.view(torch.uint8).reshape(-1), val.view(torch.uint8).reshape(-1), lab.reshape(-1),
+                        bm.class_pos.view(torch.uint8), bm.sums.view(torch.uint8)]).cpu().numpy()
+    o = 0
+    idx_h = packed[o:o + n * k * 4].view(np.int32).reshape(n, k); o += n * k * 4
+    val_h = packed[o:o + n * k * 4].view(np.float32).reshape(n, k); o += n * k * 4
+    lab_h = packed[o:o + n * k].reshape(n, k); o += n * k
+    pos_h = packed[o:o + V * 4].view(np.int32).astype(np.float64); o += V * 4
+    sums = packed[o:o + 32].view(np.float64)
+    return {"n": n, "idx": idx_h, "val": val_h, "lab": lab_h, "num_positives": pos_h,
+            "hit_sum": float(sums[1]), "perr_sum": float(sums[2]), "loss_sum": float(sums[3])}
 
 
 class EvaluationMetrics(object):
@@ -132,15 +153,70 @@ class EvaluationMetrics(object):
         self.num_class = num_class
         self.distributed = distributed
         self.group = group
+        self._dev_acc, self._dev_triplets, self._dev_examples = None, [], 0
 
     def accumulate(self, predictions, labels, loss):
+        if torch.is_tensor(predictions) and predictions.is_cuda and not self.distributed:
+            return self.accumulate_device(predictions, labels, loss)
         return self.accumulate_stats(batch_stats(predictions, labels, loss, self.top_k))
 
-    def accumulate_stats(self, stats):
+    def accumulate_device(self, predictions, labels, loss, fetch=True):
+        """GPU-resident accumulation: the batch's top-k triplets stay in device memory, the hit@1 /
+        PERR / loss sums and the per-class positives are added to device accumulators by evc_batch_metrics;
+        nothing is copied to the host until `get()`.  fetch=True reads the batch's three numbers back for the
+        log line (one 16-byte copy, the reference fetches them with every sess.run); fetch=False returns the
+        device vector [hit@1, PERR, GAP, loss] and never synchronises."""
+        p, a = _dev(predictions, labels)
+        n = int(p.shape[0])
+        if n == 0:
+            return {"hit_at_one": 0.0, "perr": 0.0, "loss": 0.0}
+        d = self._dev_acc
+        if d is None or d.B < n or d.out.device != p.device:
+            old = d
+            d = self._dev_acc = ops.BatchMetrics(max(n, old.B if old else 0), self.num_class, self.top_k, p.device,
+                                                 accumulate=True)
+            if old is not None:
+                d.class_pos.copy_(old.class_pos)
+                d.sums.copy_(old.sums)
+        out, idx, val, lab = d.run(p, a, _loss_rows(loss, n, p.device), n)
+        self._dev_triplets.append((idx, val, lab))
+        self._dev_examples += n
+        if not fetch:
+            return out
+        h = out.tolist()
+        return {"hit_at_one": h[0], "perr": h[1], "loss": h[3]}
+
+    def _flush_device(self):
+        """Move the device-resident accumulators into the host calculators (one copy per tensor, per epoch)."""
+        if self._dev_acc is None or not self._dev_triplets:
+            return
+        rows = [int(t[0].shape[0]) for t in self._dev_triplets]
+        k = self._dev_triplets[0][0].shape[1]
+        idx = torch.cat([t[0].reshape(-1) for t in self._dev_triplets]).cpu().numpy().reshape(-1, k)
+        val = torch.cat([t[1].reshape(-1) for t in self._dev_triplets]).cpu().numpy().reshape(-1, k)
+        lab = torch.cat([t[2].reshape(-1) for t in self._dev_triplets]).cpu().numpy().reshape(-1, k)
+        sums = self._dev_acc.sums.cpu().numpy()
+        pos = self._dev_acc.class_pos.cpu().numpy().astype(np.float64)
+        # batch by batch, so that ties between equal predictions keep the arrival order of the host path (the
+        # epoch's positives and sums ride on the first batch: the calculators only add them up)
+        r0 = 0
+        for i, r in enumerate(rows):
+            first = i == 0
+            self.accumulate_stats({"n": r, "idx": idx[r0:r0 + r], "val": val[r0:r0 + r], "lab": lab[r0:r0 + r],
+                                   "num_positives": pos if first else np.zeros_like(pos),
+                                   "hit_sum": float(sums[1]) if first else 0.0,
+                                   "perr_sum": float(sums[2]) if first else 0.0,
+                                   "loss_sum": float(sums[3]) if first else 0.0}, local_only=True)
+            r0 += r
+        self._dev_triplets, self._dev_examples = [], 0
+        self._dev_acc.sums.zero_()
+        self._dev_acc.class_pos.zero_()
+
+    def accumulate_stats(self, stats, local_only=False):
         """Fold the statistics of one batch (`batch_stats`) of this rank -- and, when distributed, of the same
         batch index of every other rank -- into the accumulators."""
         parts = [stats]
-        if self.distributed:
+        if self.distributed and not local_only:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
                 parts = [None] * dist.get_world_size(self.group)
@@ -183,6 +259,7 @@ class EvaluationMetrics(object):
         return {"hit_at_one": hit / n, "perr": perr / n, "loss": loss / n}
 
     def get(self):
+        self._flush_device()
         if self.num_examples <= 0:
             raise ValueError("total_sample must be positive.")
         return {"avg_hit_at_one": self.sum_hit_at_one / self.num_examples,
@@ -198,6 +275,10 @@ class EvaluationMetrics(object):
         self.map_calculator.clear()
         self.global_ap_calculator.clear()
         self.num_examples = 0
+        self._dev_triplets, self._dev_examples = [], 0
+        if self._dev_acc is not None:
+            self._dev_acc.sums.zero_()
+            self._dev_acc.class_pos.zero_()
 
 
 def format_lines(video_ids, predictions, top_k):

@@ -1,6 +1,9 @@
 """Flag side-channel of the reference models (tf.flags globals read inside create_model:
 frame_level_models.py:15-47,218-219,237-238,286-289; video_level_models.py:13-19,421;
-train.py:27-99).  Same names and defaults; set them as attributes or via ``parse``."""
+train.py:27-99, eval_finetune.py:21-60).  Same names; defaults are the reference's except where every run_*.sh
+overrides them (`lstm_layers` 2 instead of 1, `feature_names`/`feature_sizes` "rgb, audio"/"1024, 128" instead of
+"rgb"/"1024", `frame_features` True): the defaults here are the run_*.sh configuration.  Set them as attributes or
+via ``parse``.  `sampling` and `output_dir` are additions (BASELINE config #5; the converter's target directory)."""
 from __future__ import annotations
 
 
@@ -70,3 +73,16 @@ FLAGS.define("clip_gradient_norm", 1.0, "Norm to clip gradients to.")
 FLAGS.define("top_k", 20, "How many predictions to output per video.")
 FLAGS.define("feature_names", "rgb, audio", "features to use")
 FLAGS.define("feature_sizes", "1024, 128", "lengths of the feature vectors")
+# train.py:29-99 / eval_finetune.py:21-60 (launchers.py)
+FLAGS.define("train_dir", "/tmp/yt8m_model/", "The directory to save the model files in / load them from.")
+FLAGS.define("train_data_pattern", "", "File glob for the training dataset (tf.SequenceExample tfrecords).")
+FLAGS.define("eval_data_pattern", "", "File glob defining the evaluation dataset.")
+FLAGS.define("frame_features", True, "frame-level features (the H-LSTM path); run_*.sh pass True")
+FLAGS.define("start_new_model", False, "If set, training does not resume from the latest checkpoint in train_dir.")
+FLAGS.define("num_epochs", 10, "How many passes to make over the dataset before halting training.")
+FLAGS.define("num_readers", 4, "How many threads to use for reading input files.")
+FLAGS.define("gpu", 0, "GPU on which the code will run (single-process runs; torchrun sets LOCAL_RANK)")
+FLAGS.define("run_once", False, "Whether to run eval only once.")
+FLAGS.define("log_device_placement", False, "accepted for command-line parity, unused")
+FLAGS.define("sampling", "uniform", "student frame sampler: uniform | random_frames | random_sequence")
+FLAGS.define("output_dir", "", "train_convert_model: where the student-only checkpoint goes")

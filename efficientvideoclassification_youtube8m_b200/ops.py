@@ -130,11 +130,23 @@ def lstm_seq_fwd(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_al
                                      stream() if cuda_stream is None else cuda_stream), "evc_lstm_seq_fwd_steps")
 
 
+def lstm_rec_workspace_bytes(rows, H, T):
+    """Scratch of the resident-weights persistent recurrence for this shape; 0 = not eligible."""
+    return int(lib.evc_lstm_rec_workspace_bytes(rows, H, T))
+
+
+def lstm_seq_fwd_resident(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_all, gates_all, workspace):
+    check(lib.evc_lstm_seq_fwd_resident(ptr(x), x_step_stride, Kx, ptr(W), ptr(bias), rows, H, T, ptr(seq_len),
+                                        ptr(h_all), ptr(c_all), ptr(gates_all), ptr(workspace),
+                                        workspace.numel() * workspace.element_size(), stream()),
+          "evc_lstm_seq_fwd_resident")
+
+
 def lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates_all, c_all, dh_ext_all, dh_final, ld_dh_final, dc_final,
-                 ld_dc_final, dh_pass, dc, dz_all, workspace=None):
+                 ld_dc_final, dh_pass, dc, dz_all, workspace=None, dbias=None):
     check(lib.evc_lstm_seq_bwd(ptr(W), Kx, rows, H, T, ptr(seq_len), ptr(gates_all), ptr(c_all), ptr(dh_ext_all),
                                ptr(dh_final), ld_dh_final, ptr(dc_final), ld_dc_final, ptr(dh_pass), ptr(dc),
-                               ptr(dz_all), ptr(workspace),
+                               ptr(dz_all), ptr(dbias), ptr(workspace),
                                workspace.numel() * workspace.element_size() if workspace is not None else 0,
                                stream()), "evc_lstm_seq_bwd")
 
@@ -213,3 +225,31 @@ def topk(P, k, labels=None):
     if B > 0:
         check(lib.evc_topk(ptr(P), B, V, k, ptr(labels), ptr(idx), ptr(val), ptr(lab), stream()), "evc_topk")
     return idx, val, lab
+
+
+class BatchMetrics:
+    """Device-side hit@1 / PERR / GAP of one batch (eval_util.py:17-79) with reusable scratch; optionally the
+    epoch accumulators of EvaluationMetrics (class positives, sums).  `run` returns the device vector
+    [hit@1, PERR, GAP, mean loss] (no host synchronisation) and the top-k triplets."""
+
+    def __init__(self, batch, vocab, k, device, accumulate=False):
+        self.B, self.V, self.k = batch, vocab, min(k, vocab)
+        self.perr_rows = torch.zeros(batch, dtype=torch.float32, device=device)
+        self.npos_rows = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.acc = torch.zeros(1, dtype=torch.float64, device=device)
+        self.out = torch.zeros(4, dtype=torch.float32, device=device)
+        self.class_pos = torch.zeros(vocab, dtype=torch.int32, device=device) if accumulate else None
+        self.sums = torch.zeros(4, dtype=torch.float64, device=device) if accumulate else None
+
+    def run(self, P, labels_u8, loss_rows=None, n=None):
+        """P f32 [>=n, V], labels u8 [>=n, V]; the first n rows (default: all) are the batch."""
+        _cuda(P, labels_u8, loss_rows)
+        n = P.shape[0] if n is None else n
+        if n > self.B or P.shape[1] != self.V:
+            raise ValueError("batch larger than the scratch buffers / wrong number of classes")
+        idx, val, lab = topk(P[:n], self.k, labels_u8[:n])
+        if n > 0:
+            check(lib.evc_batch_metrics(ptr(P), ptr(labels_u8), n, self.V, self.k, ptr(idx), ptr(val), ptr(lab),
+                                        ptr(loss_rows), ptr(self.perr_rows), ptr(self.npos_rows), ptr(self.class_pos),
+                                        ptr(self.acc), ptr(self.out), ptr(self.sums), stream()), "evc_batch_metrics")
+        return self.out, idx, val, lab

@@ -254,16 +254,32 @@ class HLstmParams:
         self._master_stale = world > 1
         return handles
 
-    def sync_master_weights(self, rank: int, world: int, group=None) -> None:
-        """After sharded updates only the owned rows of the f32 masters are current: gather the rest
-        (needed before state_dict()/save(), not on the training path)."""
+    def sync_master_weights(self, rank: int, world: int, group=None, include_slots: bool = False) -> None:
+        """After sharded updates only the owned rows of the f32 masters (and of the Adam moments) are current:
+        gather the rest (needed before state_dict()/save()/checkpoints, not on the training path)."""
         import torch.distributed as dist
         if world <= 1 or not getattr(self, "_master_stale", False):
             return
         for n in self.matrix_names():
             r0, r1 = self.row_block(n, rank, world)
-            dist.all_gather_into_tensor(self.w[n], self.w[n][r0:r1].clone(), group=group)
-        self._master_stale = False
+            for t in ([self.w[n]] + ([self.m[n], self.v[n]] if include_slots else [])):
+                dist.all_gather_into_tensor(t, t[r0:r1].clone(), group=group)
+        if include_slots:
+            self._master_stale = False
+        else:
+            self._slots_stale = True
+            self._master_stale = False
+
+    def sync_all(self, include_slots: bool = True) -> None:
+        """Collective: make the weights (and optimizer slots) of every rank complete; no-op on one rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+            return
+        if getattr(self, "_slots_stale", False) and include_slots:
+            self._master_stale = True          # the weights were synced without the slots: gather both again
+        self.sync_master_weights(dist.get_rank(), dist.get_world_size(), include_slots=include_slots)
+        if include_slots:
+            self._slots_stale = False
 
     # ---- slim.learning.create_train_op: per-variable clip_by_norm + Adam (train.py:329-334)
     def begin_apply(self, lr: float, beta1: float = 0.9, beta2: float = 0.999) -> None:

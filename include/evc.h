@@ -110,16 +110,30 @@ int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, int Kx, const
  * full-occupancy cell kernel; without one (NULL) every step uses the fused-epilogue kernel. */
 long long evc_lstm_workspace_bytes(int rows, int H, int Kx);
 
+/* The same layer with the recurrence as ONE persistent launch whose CTAs keep their slice of the recurrent
+ * weights (4 gate columns x 16 units x H rows of `W`, 128 KB at H = 1024) resident in shared memory for all T
+ * steps (csrc/evc_rec.cuh; small-row regime: RNN_L2, the student's RNN_L1).  The input half of the matmul is
+ * hoisted into one GEMM over all steps (x must be contiguous over the steps: x_step_stride == rows*Kx).
+ * evc_lstm_rec_workspace_bytes returns 0 when the shape is not eligible (too many rows for one wave of
+ * co-resident CTAs, H too large for the resident slice); workspace must be 1024-byte aligned.  The caller must
+ * not run two of these launches concurrently on different streams (all CTAs of a launch must be co-resident). */
+long long evc_lstm_rec_workspace_bytes(int rows, int H, int T);
+int evc_lstm_seq_fwd_resident(const void* x, long long x_step_stride, int Kx, const void* W, const float* bias,
+                              int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
+                              void* gates_all, void* workspace, long long workspace_bytes, void* stream);
+
 /* Backward twin: for t = T-1..0 one fused kernel computing dz_{t+1} * Wh^T on tcgen05 and, in the
  * epilogue, the gate gradients dz_t (bf16 [T,rows,4H]) with the sequence_length mask.
  * dh_ext_all f32 [T,rows,H] (nullable): gradient w.r.t. the cell output at each step (from the cell
  * above).  dh_final/dc_final (nullable, row pitches ld_*): gradient w.r.t. the final state.
  * dh_pass, dc: f32 [rows,H] scratch.  With a workspace the recurrent dgrad runs as a (split-K) GEMM
- * + a full-occupancy cell kernel (measured faster); NULL selects the fused-epilogue kernel. */
+ * + a full-occupancy cell kernel (measured faster); NULL selects the fused-epilogue kernel.
+ * dbias f32 [4H] (nullable, workspace path only): the bias gradient = column sums of dz over all steps and rows,
+ * accumulated by the cell kernel while it writes dz (zeroed by this call). */
 int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len, const void* gates_all,
                      const float* c_all, const float* dh_ext_all, const float* dh_final, long long ld_dh_final,
                      const float* dc_final, long long ld_dc_final, float* dh_pass, float* dc, void* dz_all,
-                     void* workspace, long long workspace_bytes, void* stream);
+                     float* dbias, void* workspace, long long workspace_bytes, void* stream);
 
 /* final MultiRNNCell state [c0|h0|c1|h1] (state_is_tuple=False; frame_level_models.py:252,257). */
 int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,
@@ -177,6 +191,16 @@ int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, con
  * lower class index first among equals), their values and (nullable) labels. */
 int evc_topk(const float* P, int B, int V, int k, const unsigned char* labels, int* idx_out, float* val_out,
              unsigned char* lab_out, void* stream);
+
+/* ---- the per-batch training / evaluation metrics of eval_util.py on the device, given evc_topk's output for the
+ * same batch (idx/val/lab [B,k]): out[0] = hit@1 (eval_util.py:17-31), out[1] = PERR (:34-59), out[2] = GAP over
+ * the pooled top-k triplets (:61-79, ties ordered by (class, video)), out[3] = mean of loss_rows (nullable).
+ * Scratch: perr_rows f32 [B], npos_rows int32 [B], acc double[1] (zero before the first call; reset by the call).
+ * Epoch accumulators (nullable): class_pos int32 [V] += positives per class (:114), sums double[4] += (videos,
+ * hit sum, perr sum, loss sum) -- what EvaluationMetrics.accumulate keeps (:139-167). */
+int evc_batch_metrics(const float* P, const unsigned char* labels, int B, int V, int k, const int* idx,
+                      const float* val, const unsigned char* lab, const float* loss_rows, float* perr_rows,
+                      int* npos_rows, int* class_pos, double* acc, float* out, double* sums, void* stream);
 
 #ifdef __cplusplus
 }

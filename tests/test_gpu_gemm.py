@@ -102,7 +102,11 @@ def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
     dh_pass = torch.zeros(rows, H, device=dev)
     dc = torch.zeros(rows, H, device=dev)
     dh_ext_masked = torch.where(live_all, dh_ext, torch.zeros_like(dh_ext)).contiguous()
-    ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc, dz, ws)
+    # workspace path: the bias gradient is accumulated by the cell kernel while it writes dz (pre-filled with
+    # garbage: the call zeroes it)
+    db_fused = torch.full((4 * H,), 7.0, device=dev) if use_ws else None
+    ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc, dz, ws,
+                     dbias=db_fused)
     # wgrad: dW = [x | h_prev]^T dz ; dX = dz Wx^T ; db = colsum dz
     dW = torch.zeros(Kx + H, 4 * H, device=dev)
     R = T * rows
@@ -119,3 +123,57 @@ def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
     assert rel(dW, gW) < 3e-2, rel(dW, gW)
     assert rel(dX.view(T, rows, Kx), gx) < 3e-2, rel(dX.view(T, rows, Kx), gx)
     assert rel(db, gb) < 3e-2, rel(db, gb)
+    if use_ws:      # same sums of the same bf16 values, only the float summation order differs
+        assert rel(db_fused, gb) < 3e-2
+        assert (db_fused - db).abs().max().item() <= 1e-4 * db.abs().max().item() + 1e-6
+    else:
+        with pytest.raises(Exception, match="bias gradient"):
+            ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc,
+                             dz, None, dbias=db)
+
+
+@pytest.mark.parametrize("rows,Kx,H,T,train", [(256, 4096, 1024, 6, True), (1280, 1152, 1024, 6, True),
+                                               (200, 128, 128, 5, True), (128, 256, 256, 3, False),
+                                               (700, 1024, 1024, 4, True), (2048, 128, 1024, 2, False)])
+def test_lstm_seq_fwd_resident_matches_per_step_path(rows, Kx, H, T, train):
+    """The persistent resident-weights recurrence (evc_lstm_seq_fwd_resident: hoisted input projection + one launch
+    for all T steps, Wh slices in shared memory) against the f64 reference and against the per-step split-K path:
+    RNN_L2 shape (256 rows, Kx = 4H), the student's RNN_L1 (1280 rows: 5 tiles per CTA), partial tiles, one row
+    group, ragged / zero lengths, with and without saved gates."""
+    from efficientvideoclassification_youtube8m_b200 import ops
+    torch.manual_seed(1)
+    dev = "cuda"
+    need = ops.lstm_rec_workspace_bytes(rows, H, T)
+    assert need > 0
+    assert ops.lstm_rec_workspace_bytes(5120, 1024, 15) == 0          # the teacher's RNN_L1: too many rows for one wave
+    raw = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+    ws_rec = raw[(-raw.data_ptr()) % 1024:][:need]
+    ws = torch.empty(ops.lstm_workspace_bytes(rows, H, Kx), dtype=torch.uint8, device=dev)
+    x = (torch.randn(T, rows, Kx, device=dev) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)).to(torch.bfloat16)
+    b = torch.randn(4 * H, device=dev) * 0.1
+    seq_len = torch.randint(0, T + 1, (rows,), device=dev, dtype=torch.int32)
+    seq_len[:4] = torch.tensor([0, 1, T, T - 1], dtype=torch.int32)
+
+    def run(fn, *extra):
+        h_all = torch.zeros(T + 1, rows, H, dtype=torch.bfloat16, device=dev)
+        c_all = torch.zeros(T + 1, rows, H, device=dev)
+        gates = torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev) if train else None
+        fn(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, *extra)
+        torch.cuda.synchronize()
+        return h_all, c_all, gates
+
+    h1, c1, g1 = run(ops.lstm_seq_fwd_resident, ws_rec)
+    h2, c2, g2 = run(ops.lstm_seq_fwd, ws)
+    c_ref, h_ref, _ = _lstm_ref(x.double(), W.double(), b.double(), seq_len, T, H)
+    assert (c1[T].double() - c_ref).abs().max().item() < 2e-2
+    assert (h1[T].double() - h_ref).abs().max().item() < 2e-2
+    # the two paths differ only in where the f32 partial sums are rounded (Zx + bias is formed first here)
+    assert (c1 - c2).abs().max().item() < 2e-3 and (h1.float() - h2.float()).abs().max().item() < 2e-2
+    if train:
+        live = (torch.arange(T, device=dev).view(T, 1) < seq_len.view(1, rows)).unsqueeze(2)
+        assert ((g1.float() - g2.float()) * live).abs().max().item() < 2e-2
+    assert torch.all(h1[:, 0] == 0) and torch.all(c1[:, 0] == 0)        # the zero-length row never leaves the zero state
+    # a second run over the same buffers (flags are reset by the call): deterministic, bit-identical
+    h3, c3, _ = run(ops.lstm_seq_fwd_resident, ws_rec)
+    assert torch.equal(h1, h3) and torch.equal(c1, c3)

