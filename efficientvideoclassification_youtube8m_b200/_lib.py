@@ -18,8 +18,8 @@ SIGNATURES = {
     "evc_last_error": [],
     "evc_launch_count": [],
     "evc_debug_set": [I],
-    "evc_frames_pack": [P, I, I, I, P, I, I, I, I, P, P, P],
-    "evc_frames_pack_u8": [P, P, I, I, I, P, I, I, I, I, P, P, P],
+    "evc_frames_pack": [P, I, I, I, P, I, I, I, I, P, P, P, P],
+    "evc_frames_pack_u8": [P, P, I, I, I, P, I, I, I, I, P, P, P, P],
     "evc_num_frames_student": [P, I, I, I, P, P],
     "evc_lstm_lengths": [P, I, I, I, I, P, P, P],
     "evc_random_frame_index": [P, P, I, I, P, P],
@@ -27,25 +27,26 @@ SIGNATURES = {
     "evc_sampled_lengths": [P, I, I, P, P],
     "evc_random_uniform": [C.c_ulonglong, C.c_ulonglong, P, L, P],
     "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
+    "evc_gemm_bf16x2": [P, P, I, L, P, P, I, L, I, I, I, P, I, L, P, I, I, P],
     "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
-    "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P],
-    "evc_lstm_workspace_bytes": [I, I, I],
+    "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P, P, P, P, P],
+    "evc_lstm_workspace_bytes": [I, I, I, I],
     "evc_lstm_rec_workspace_bytes": [I, I, I],
     "evc_lstm_seq_fwd_resident": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
-    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P, P, L, P],
-    "evc_state_pack": [P, P, P, P, I, I, P, P, P],
-    "evc_cast_bf16": [P, L, I, I, P, P],
+    "evc_lstm_seq_bwd": [P, I, I, I, I, P, P, P, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P],
+    "evc_state_pack": [P, P, P, P, I, I, P, P, P, P, P, P],
+    "evc_cast_bf16": [P, L, I, I, P, P, P],
     "evc_fill_f32": [P, L, F, P],
     "evc_moe_mix_fwd": [P, L, P, L, I, I, I, P, P],
-    "evc_moe_mix_bwd": [P, L, P, L, P, I, I, I, P, L, P, L, P],
+    "evc_moe_mix_bwd": [P, L, P, L, P, I, I, I, P, L, P, L, P, P, P],
     "evc_ce_kl_loss": [P, P, P, I, I, F, F, P, P, P, P],
-    "evc_moe_mix_loss": [P, L, P, L, P, P, I, I, I, F, F, P, P, P, P, L, P, L, P],
+    "evc_moe_mix_loss": [P, L, P, L, P, P, I, I, I, F, F, P, P, P, P, L, P, L, P, P, P],
     "evc_reduce_rows": [P, I, F, P, P],
     "evc_adam_lr": [P, F, F, F, P, P],
     "evc_rep_loss": [P, P, I, I, F, P, P, P],
     "evc_colsum_bf16": [P, L, I, L, P, P],
     "evc_sumsq": [P, P, F, L, P, P, P],
-    "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P],
+    "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P, P],
     "evc_batch_metrics": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "evc_topk": [P, I, I, I, P, P, P, P, P],
 }

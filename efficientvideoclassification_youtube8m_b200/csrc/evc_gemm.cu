@@ -116,7 +116,13 @@ static int g_debug = 0;       // profiling experiments only (evc_debug_set)
 
 template <int A_MN, int B_MN, int BN, int EPI, int CS>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c,
-                  const GemmArgs& args, cudaStream_t stream) {
+                  const GemmArgs& args_in, cudaStream_t stream, const CUtensorMap* a1lo = nullptr,
+                  const CUtensorMap* a2lo = nullptr, const CUtensorMap* blo = nullptr) {
+  GemmArgs args = args_in;
+  args.segments = (a1lo != nullptr && blo != nullptr) ? 3 : 1;
+  const CUtensorMap& xa1 = a1lo ? *a1lo : a1;
+  const CUtensorMap& xa2 = a2lo ? *a2lo : (a1lo ? *a1lo : a2);
+  const CUtensorMap& xb = blo ? *blo : b;
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, CS>;
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
@@ -139,7 +145,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (g_debug & 256) ? 1 : 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, c, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, c, xa1, xa2, xb, args);
   count_launch();
   if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(gemm_kernel)");
   return check_launch("gemm_kernel");
@@ -153,8 +159,13 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M, int N,
                       int K, void* C, int c_bf16, long long ldc, const float* bias, int split_k, int accumulate,
                       cudaStream_t stream, int force_bn = 0, long long split_stride = 0, int* splits_out = nullptr,
-                      const void* A2 = nullptr, int K1 = 0) {
+                      const void* A2 = nullptr, int K1 = 0, const void* A_lo = nullptr, const void* B_lo = nullptr,
+                      const void* A2_lo = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "gemm: empty problem");
+  // split-bf16 "precise" product: both residual planes or none (same shapes / pitches as the hi planes)
+  const bool x2 = A_lo != nullptr || B_lo != nullptr;
+  if (x2 && (A_lo == nullptr || B_lo == nullptr || (A2 != nullptr) != (A2_lo != nullptr)))
+    return set_error(EVC_ERR_ARG, "gemm: split-bf16 mode needs the lo plane of every operand");
   if (split_k < 1) split_k = 1;
   if ((split_k > 1 || accumulate) && c_bf16) return set_error(EVC_ERR_ARG, "gemm: split-K/accumulate needs f32 C");
   const int bn = force_bn ? force_bn : ((N > 128) ? 256 : 128);
@@ -181,6 +192,16 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
     rc = make_tmap_a(&ta2, A2, a_mn, K - K1, M, K - K1);
     if (rc) return rc;
   }
+  CUtensorMap talo, ta2lo, tblo;
+  if (x2) {
+    rc = make_tmap_a(&talo, A_lo, a_mn, A2 ? K1 : lda, M, A2 ? K1 : K);
+    if (rc) return rc;
+    ta2lo = talo;
+    if (A2) {
+      rc = make_tmap_a(&ta2lo, A2_lo, a_mn, K - K1, M, K - K1);
+      if (rc) return rc;
+    }
+  }
   int cs = (g.tiles_m >= 2) ? kCluster : 1;
   if (cs > 1) {   // pairing must not add a round over the SMs (odd tile counts pad to a dummy tile)
     const long long w1 = static_cast<long long>(g.tiles_m) * g.tiles_n * g.split_k;
@@ -191,6 +212,13 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   }
   rc = make_tmap_b(&tb, B, b_mn, ldb, N, K, bn, cs);
   if (rc) return rc;
+  if (x2) {
+    rc = make_tmap_b(&tblo, B_lo, b_mn, ldb, N, K, bn, cs);
+    if (rc) return rc;
+  }
+  const CUtensorMap* pa = x2 ? &talo : nullptr;
+  const CUtensorMap* pa2 = x2 ? &ta2lo : nullptr;
+  const CUtensorMap* pb = x2 ? &tblo : nullptr;
   // C through TMA bulk stores when its layout allows (16-byte aligned rows) and no atomics are needed
   CUtensorMap tc = ta;
   const int eb = c_bf16 ? 2 : 4;
@@ -208,10 +236,10 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
 #define EVC_DISPATCH(AM, BMN)                                                                    \
   if (a_mn == AM && b_mn == BMN) {                                                                \
     if (cs == 1)                                                                                  \
-      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream)           \
-                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream);          \
-    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream)      \
-                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream);     \
+      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream, pa, pa2, pb)           \
+                       : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream, pa, pa2, pb);          \
+    return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream, pa, pa2, pb)      \
+                     : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream, pa, pa2, pb);     \
   }
   EVC_DISPATCH(0, 0)
   EVC_DISPATCH(0, 1)
@@ -232,6 +260,15 @@ extern "C" int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
                              const float* bias, int split_k, int accumulate, void* stream) {
   return gemm_store(A, a_mn_major, lda, B, b_mn_major, ldb, M, N, K, C, c_is_bf16, ldc, bias, split_k, accumulate,
                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int evc_gemm_bf16x2(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B,
+                               const void* B_lo, int b_mn_major, long long ldb, int M, int N, int K, void* C,
+                               int c_is_bf16, long long ldc, const float* bias, int split_k, int accumulate,
+                               void* stream) {
+  if (A_lo == nullptr || B_lo == nullptr) return set_error(EVC_ERR_ARG, "gemm_bf16x2: lo planes required");
+  return gemm_store(A, a_mn_major, lda, B, b_mn_major, ldb, M, N, K, C, c_is_bf16, ldc, bias, split_k, accumulate,
+                    static_cast<cudaStream_t>(stream), 0, 0, nullptr, nullptr, 0, A_lo, B_lo);
 }
 
 // ------------------------------------------------------------------ BasicLSTM layer, forward over T steps
@@ -256,9 +293,10 @@ static int pick_split(int tiles, int kb_total) {
   return best;
 }
 
-extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
+extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx, int precise) {
   // forward small-row path: S x rows x 4H f32 ; backward: S x rows x H f32
-  int sf = (rows <= 1024) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
+  // (precise = split-bf16 mode: every forward step goes through the slab path, whatever the row count)
+  int sf = (rows <= 1024 || precise) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
   const int sb = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
   const long long f = static_cast<long long>(sf) * rows * 4 * H * 4;
   const long long b = static_cast<long long>(sb) * rows * H * 4;
@@ -271,9 +309,18 @@ extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx) {
 extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, int Kx, const void* W,
                                       const float* bias, int rows, int H, int T, int t_begin, int t_end,
                                       const int* seq_len, void* h_all, float* c_all, void* gates_all,
-                                      void* workspace, long long workspace_bytes, void* stream_) {
+                                      void* workspace, long long workspace_bytes, const void* x_lo, const void* W_lo,
+                                      void* h_lo_all, void* gates_lo_all, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: empty problem");
+  // split-bf16 "precise" mode: the residual planes of x, W and h (and of the saved gates when gates are saved)
+  const bool x2 = x_lo != nullptr || W_lo != nullptr || h_lo_all != nullptr;
+  if (x2 && (x_lo == nullptr || W_lo == nullptr || h_lo_all == nullptr || (gates_all != nullptr) != (gates_lo_all != nullptr)))
+    return set_error(EVC_ERR_ARG, "lstm_seq_fwd: split-bf16 mode needs the lo planes of x, W, h (and gates)");
+  if (x2 && workspace == nullptr) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: split-bf16 mode needs a workspace");
+  const __nv_bfloat16* xl = static_cast<const __nv_bfloat16*>(x_lo);
+  __nv_bfloat16* hl = static_cast<__nv_bfloat16*>(h_lo_all);
+  __nv_bfloat16* gl = static_cast<__nv_bfloat16*>(gates_lo_all);
   if (t_begin < 0 || t_end > T || t_begin >= t_end) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: bad step range");
   if (H % 64 != 0 || Kx % 64 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_fwd: H and Kx must be multiples of 64");
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
@@ -281,7 +328,7 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
   __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
   const long long RH = static_cast<long long>(rows) * H;
   int rc;
-  if (rows <= 1024 && workspace != nullptr) {
+  if ((rows <= 1024 || x2) && workspace != nullptr) {
     // Small-row steps (RNN_L2, student): one 128x256 tile per CTA would serialise the whole K on a few
     // SMs.  Split K over the SMs into f32 partial slabs, then one full-occupancy cell kernel sums
     // the slabs and applies bias / gates / state update / length mask.
@@ -294,11 +341,15 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
         return set_error(EVC_ERR_ARG, "lstm_seq_fwd: workspace too small (evc_lstm_workspace_bytes)");
       int splits = 1;
       rc = gemm_store(xb + t * x_step_stride, 0, Kx, W, 1, 4LL * H, rows, 4 * H, K, part, 0, 4LL * H, nullptr, want, 0,
-                      stream, 256, slab, &splits, (t == 0) ? nullptr : hb + t * RH, Kx);
+                      stream, 256, slab, &splits, (t == 0) ? nullptr : hb + t * RH, Kx,
+                      x2 ? xl + t * x_step_stride : nullptr, x2 ? W_lo : nullptr,
+                      (x2 && t > 0) ? hl + t * RH : nullptr);
       if (rc) return rc;
       rc = launch_lstm_cell_fwd(part, splits, slab, bias, (t == 0) ? nullptr : c_all + t * RH,
                                 (t == 0) ? nullptr : hb + t * RH, seq_len, t, rows, H, c_all + (t + 1) * RH,
-                                hb + (t + 1) * RH, gb ? gb + t * RH * 4 : nullptr, stream);
+                                hb + (t + 1) * RH, gb ? gb + t * RH * 4 : nullptr, stream,
+                                (x2 && t > 0) ? hl + t * RH : nullptr, x2 ? hl + (t + 1) * RH : nullptr,
+                                (x2 && gl) ? gl + t * RH * 4 : nullptr);
       if (rc) return rc;
     }
     return EVC_OK;
@@ -444,7 +495,7 @@ extern "C" int evc_lstm_seq_fwd(const void* x, long long x_step_stride, int Kx, 
                                 int rows, int H, int T, const int* seq_len, void* h_all, float* c_all,
                                 void* gates_all, void* workspace, long long workspace_bytes, void* stream_) {
   return evc_lstm_seq_fwd_steps(x, x_step_stride, Kx, W, bias, rows, H, T, 0, T, seq_len, h_all, c_all, gates_all,
-                                workspace, workspace_bytes, stream_);
+                                workspace, workspace_bytes, nullptr, nullptr, nullptr, nullptr, stream_);
 }
 
 // ------------------------------------------------------------------ BasicLSTM layer, backward over T steps
@@ -452,9 +503,16 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
                                 const void* gates_all, const float* c_all, const float* dh_ext_all,
                                 const float* dh_final, long long ld_dh_final, const float* dc_final,
                                 long long ld_dc_final, float* dh_pass, float* dc, void* dz_all, float* dbias,
-                                void* workspace, long long workspace_bytes, void* stream_) {
+                                void* workspace, long long workspace_bytes, const void* W_lo, const void* gates_lo_all,
+                                void* dz_lo_all, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows <= 0 || T <= 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: empty problem");
+  const bool x2 = W_lo != nullptr || gates_lo_all != nullptr || dz_lo_all != nullptr;
+  if (x2 && (W_lo == nullptr || gates_lo_all == nullptr || dz_lo_all == nullptr || workspace == nullptr))
+    return set_error(EVC_ERR_ARG, "lstm_seq_bwd: split-bf16 mode needs the lo planes of W, gates, dz and a workspace");
+  const __nv_bfloat16* gl = static_cast<const __nv_bfloat16*>(gates_lo_all);
+  __nv_bfloat16* zl = static_cast<__nv_bfloat16*>(dz_lo_all);
+  const __nv_bfloat16* whl = x2 ? static_cast<const __nv_bfloat16*>(W_lo) + static_cast<long long>(Kx) * 4 * H : nullptr;
   if (dbias != nullptr && workspace == nullptr)
     return set_error(EVC_ERR_UNSUPPORTED, "lstm_seq_bwd: the bias gradient is fused into the cell kernel of the "
                                           "workspace path (use evc_colsum_bf16 over dz with the fused-epilogue path)");
@@ -481,13 +539,14 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
       int splits = 0;
       if (!last) {
         int rc = gemm_store(zb + (t + 1) * RH * 4, 0, 4LL * H, wh, 0, 4LL * H, rows, H, 4 * H, part, 0, H, nullptr,
-                            want, 0, stream, 256, RH, &splits);
+                            want, 0, stream, 256, RH, &splits, nullptr, 0, x2 ? zl + (t + 1) * RH * 4 : nullptr, whl);
         if (rc) return rc;
       }
       int rc = launch_lstm_cell_bwd(part, splits, RH, gb + t * RH * 4, (t == 0) ? nullptr : c_all + t * RH,
                                     dh_ext_all ? dh_ext_all + t * RH : nullptr, H, last ? dh_final : dh_pass,
                                     last ? ld_dh_final : H, last ? dc_final : dc, last ? ld_dc_final : H, seq_len, t,
-                                    rows, H, zb + t * RH * 4, dc, dh_pass, dbias, stream);
+                                    rows, H, zb + t * RH * 4, dc, dh_pass, dbias, stream,
+                                    x2 ? gl + t * RH * 4 : nullptr, x2 ? zl + t * RH * 4 : nullptr);
       if (rc) return rc;
     }
     return EVC_OK;

@@ -54,6 +54,8 @@ struct GemmArgs {
   int kb_a1;           // k blocks taken from tensor map A1; the remainder comes from A2
   int kb_per_split;
   int debug;           // profiling experiments only (evc_debug_set): 1024 = release the dependent grid at kernel start
+  int segments;        // 1: A*B.  3: split-bf16 "precise" product A_hi*B_hi + A_hi*B_lo + A_lo*B_hi -- the k range is
+                       // walked three times into the same f32 accumulator, operands from the hi / lo tensor maps
   // ---- EPI_STORE
   void* C;
   long long ldc;
@@ -152,7 +154,9 @@ __device__ __forceinline__ void flush_bf16(const float* st, __nv_bfloat16* g, lo
 template <int A_MN, int B_MN, int BN, int EPI, int CS>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+            const __grid_constant__ CUtensorMap tmA1lo, const __grid_constant__ CUtensorMap tmA2lo,
+            const __grid_constant__ CUtensorMap tmBlo, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -176,6 +180,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (args.segments > 1) {
+      tma_prefetch_desc(&tmA1lo);
+      tma_prefetch_desc(&tmA2lo);
+      tma_prefetch_desc(&tmBlo);
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], CS);   // every CTA of the cluster must have consumed the slot
@@ -222,13 +231,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         const int ks = w / (tiles_mc * args.tiles_n);
         const int kb0 = ks * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+        for (int seg = 0; seg < args.segments; ++seg)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const bool first = kb < args.kb_a1;
-          const CUtensorMap* ta = first ? &tmA1 : &tmA2;
+          // segment 0: hi*hi, 1: hi*lo, 2: lo*hi
+          const CUtensorMap* ta = (seg == 2) ? (first ? &tmA1lo : &tmA2lo) : (first ? &tmA1 : &tmA2);
+          const CUtensorMap* tb = (seg == 1) ? &tmBlo : &tmB;
           const int ka = (first ? kb : kb - args.kb_a1) * BK;
           if (A_MN) {
             tma_load_2d(sa, ta, &full_bar[stage], m_blk * BM, ka);
@@ -243,14 +255,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             for (int j = 0; j < NB / CS; ++j) {
               const int i = cta_rank * (NB / CS) + j;
               const int n = (EPI == EPI_LSTM_FWD) ? (i * args.H + n_blk * 64) : (n_blk * BN + i * 64);
-              if (CS > 1) tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[stage], n, kbk, kMcMask);
-              else tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], n, kbk);
+              if (CS > 1) tma_load_2d_mc(sb + i * 8192, tb, &full_bar[stage], n, kbk, kMcMask);
+              else tma_load_2d(sb + i * 8192, tb, &full_bar[stage], n, kbk);
             }
           } else {
             constexpr int RB = BN / CS;            // rows of the K-major B tile loaded by this CTA
-            if (CS > 1) tma_load_2d_mc(sb + cta_rank * RB * 128, &tmB, &full_bar[stage], kbk,
+            if (CS > 1) tma_load_2d_mc(sb + cta_rank * RB * 128, tb, &full_bar[stage], kbk,
                                        n_blk * BN + cta_rank * RB, kMcMask);
-            else tma_load_2d(sb, &tmB, &full_bar[stage], kbk, n_blk * BN);
+            else tma_load_2d(sb, tb, &full_bar[stage], kbk, n_blk * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -272,6 +284,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        for (int seg = 0; seg < args.segments; ++seg)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -281,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, da, db, idesc, (seg > 0 || kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CS > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
           else umma_commit(&empty_bar[stage]);

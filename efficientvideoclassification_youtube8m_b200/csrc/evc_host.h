@@ -18,9 +18,11 @@ int opt_in_smem(const void* func, int bytes);       // once per (kernel, device)
 // elementwise BasicLSTM cell kernels (evc_kernels.cu) used by the split-K recurrence paths
 int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, const float* bias, const float* c_prev,
                          const void* h_prev, const int* seq_len, int t, int rows, int H, float* c_out, void* h_out,
-                         void* gates, cudaStream_t stream);
+                         void* gates, cudaStream_t stream, const void* h_prev_lo = nullptr, void* h_out_lo = nullptr,
+                         void* gates_lo = nullptr);
 int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, const void* gates, const float* c_prev,
                          const float* dh_ext, long long ld_dh_ext, const float* dh_pass_in, long long ld_dh_pass_in,
                          const float* dc_in, long long ld_dc_in, const int* seq_len, int t, int rows, int H,
-                         void* dz_out, float* dc_out, float* dh_pass_out, float* dbias, cudaStream_t stream);
+                         void* dz_out, float* dc_out, float* dh_pass_out, float* dbias, cudaStream_t stream,
+                         const void* gates_lo = nullptr, void* dz_lo = nullptr);
 }  // namespace evc

@@ -55,6 +55,42 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {  // sh: 32 floa
   return sh[0];
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+__device__ __forceinline__ void unpack4_bf16(uint2 w, float* v) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+// Split-bf16 ("precise" mode) operand planes: v = hi + lo with hi = bf16(v), lo = bf16(v - hi); the GEMMs then
+// form A_hi*B_hi + A_hi*B_lo + A_lo*B_hi in f32 (~16 mantissa bits per operand instead of 8).
+__device__ __forceinline__ void store4_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, const float* v) {
+  const uint2 h = pack4_bf16(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<uint2*>(hi + off) = h;
+  if (lo != nullptr) {
+    float q[4];
+    unpack4_bf16(h, q);
+    *reinterpret_cast<uint2*>(lo + off) = pack4_bf16(v[0] - q[0], v[1] - q[1], v[2] - q[2], v[3] - q[3]);
+  }
+}
+__device__ __forceinline__ void load4_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long off, float* v) {
+  unpack4_bf16(*reinterpret_cast<const uint2*>(hi + off), v);
+  if (lo != nullptr) {
+    float q[4];
+    unpack4_bf16(*reinterpret_cast<const uint2*>(lo + off), q);
+    v[0] += q[0]; v[1] += q[1]; v[2] += q[2]; v[3] += q[3];
+  }
+}
+__device__ __forceinline__ void store1_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, float v) {
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  hi[off] = h;
+  if (lo != nullptr) lo[off] = __float2bfloat16(v - __bfloat162float(h));
+}
+
 
 // --------------------------------------------------------------------------------------
 // train.py:256 l2_normalize + train.py:265-272 gather (or model_utils.py:34-58 gather_nd),
@@ -64,7 +100,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 __global__ void frames_pack_kernel(const float* __restrict__ src, int B, int T, int D,
                                    const int* __restrict__ frame_idx, int idx_per_batch, int K, int C,
                                    int normalize, __nv_bfloat16* __restrict__ out_bf16,
-                                   float* __restrict__ out_f32) {
+                                   float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_lo) {
   PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,11 +127,8 @@ __global__ void frames_pack_kernel(const float* __restrict__ src, int B, int T, 
     float4 v = __ldg(s + i);
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     if (ob) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(ob + 4 * i) = u;
+      const float q[4] = {v.x, v.y, v.z, v.w};
+      store4_split(ob, out_lo ? out_lo + (ob - out_bf16) : nullptr, 4 * i, q);
     }
     if (of) of[i] = v;
   }
@@ -108,7 +141,7 @@ __global__ void frames_pack_kernel(const float* __restrict__ src, int B, int T, 
 __global__ void frames_pack_u8_kernel(const uint8_t* __restrict__ src, const int* __restrict__ num_frames, int B,
                                       int T, int D, const int* __restrict__ frame_idx, int idx_per_batch, int K,
                                       int C, int normalize, __nv_bfloat16* __restrict__ out_bf16,
-                                      float* __restrict__ out_f32) {
+                                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_lo) {
   PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,11 +178,8 @@ __global__ void frames_pack_u8_kernel(const uint8_t* __restrict__ src, const int
       v.w = __fadd_rn(__fmul_rn(q.w, scalar), bias) * scale;
     }
     if (ob) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(ob + 4 * i) = u;
+      const float q[4] = {v.x, v.y, v.z, v.w};
+      store4_split(ob, out_lo ? out_lo + (ob - out_bf16) : nullptr, 4 * i, q);
     }
     if (of) of[i] = v;
   }
@@ -240,19 +270,23 @@ __global__ void random_uniform_kernel(unsigned long long seed, unsigned long lon
 // (c, h) of both cells into the 4H-wide row that RNN_L2 / MoE / L_REP consume.
 __global__ void state_pack_kernel(const float* __restrict__ c0, const __nv_bfloat16* __restrict__ h0,
                                   const float* __restrict__ c1, const __nv_bfloat16* __restrict__ h1, long long n,
-                                  int H, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+                                  int H, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                  const __nv_bfloat16* __restrict__ h0_lo, const __nv_bfloat16* __restrict__ h1_lo,
+                                  __nv_bfloat16* __restrict__ out_lo) {
   PDL_PROLOGUE();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long r = i / H;
   const int u = static_cast<int>(i % H);
-  const float vc0 = c0[i], vh0 = __bfloat162float(h0[i]), vc1 = c1[i], vh1 = __bfloat162float(h1[i]);
+  const float vc0 = c0[i], vc1 = c1[i];
+  float vh0 = __bfloat162float(h0[i]), vh1 = __bfloat162float(h1[i]);
+  if (h0_lo) { vh0 += __bfloat162float(h0_lo[i]); vh1 += __bfloat162float(h1_lo[i]); }
   const long long o = r * 4 * H + u;
   if (out_bf16) {
-    out_bf16[o] = __float2bfloat16(vc0);
-    out_bf16[o + H] = h0[i];
-    out_bf16[o + 2 * H] = __float2bfloat16(vc1);
-    out_bf16[o + 3 * H] = h1[i];
+    store1_split(out_bf16, out_lo, o, vc0);
+    store1_split(out_bf16, out_lo, o + H, vh0);
+    store1_split(out_bf16, out_lo, o + 2 * H, vc1);
+    store1_split(out_bf16, out_lo, o + 3 * H, vh1);
   }
   if (out_f32) {
     out_f32[o] = vc0;
@@ -262,18 +296,6 @@ __global__ void state_pack_kernel(const float* __restrict__ c0, const __nv_bfloa
   }
 }
 
-__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
-__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-}
-__device__ __forceinline__ void unpack4_bf16(uint2 w, float* v) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
 // BasicLSTMCell forward on split-K partial pre-activations (small-row recurrence steps):
 //   z = sum_s z_part[s] + bias ; i,j,f,o ; c' = c*sigmoid(f+1) + sigmoid(i)*tanh(j) ; h' = tanh(c')*sigmoid(o)
 // with the dynamic_rnn copy-through for rows past their sequence_length.  Thread = (row, 4 units).
@@ -281,7 +303,9 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, lo
                                      const float* __restrict__ bias, const float* __restrict__ c_prev,
                                      const __nv_bfloat16* __restrict__ h_prev, const int* __restrict__ seq_len,
                                      int t, int rows, int H, float* __restrict__ c_out,
-                                     __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ gates) {
+                                     __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ gates,
+                                     const __nv_bfloat16* __restrict__ h_prev_lo, __nv_bfloat16* __restrict__ h_out_lo,
+                                     __nv_bfloat16* __restrict__ gates_lo) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL (see evc_ptx.cuh)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -297,6 +321,11 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, lo
     uint2 hp = make_uint2(0u, 0u);
     if (h_prev != nullptr) hp = *reinterpret_cast<const uint2*>(h_prev + off);
     *reinterpret_cast<uint2*>(h_out + off) = hp;
+    if (h_out_lo != nullptr) {
+      uint2 hl = make_uint2(0u, 0u);
+      if (h_prev_lo != nullptr) hl = *reinterpret_cast<const uint2*>(h_prev_lo + off);
+      *reinterpret_cast<uint2*>(h_out_lo + off) = hl;
+    }
     return;
   }
   float z[4][4];
@@ -325,13 +354,13 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, lo
     hn[k] = tanh_(cn[k]) * go[k];
   }
   *reinterpret_cast<float4*>(c_out + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-  *reinterpret_cast<uint2*>(h_out + off) = pack4_bf16(hn[0], hn[1], hn[2], hn[3]);
+  store4_split(h_out, h_out_lo, off, hn);
   if (gates != nullptr) {
-    __nv_bfloat16* gp = gates + static_cast<long long>(r) * 4 * H + u;
-    *reinterpret_cast<uint2*>(gp + 0 * H) = pack4_bf16(gi[0], gi[1], gi[2], gi[3]);
-    *reinterpret_cast<uint2*>(gp + 1 * H) = pack4_bf16(gj[0], gj[1], gj[2], gj[3]);
-    *reinterpret_cast<uint2*>(gp + 2 * H) = pack4_bf16(gf[0], gf[1], gf[2], gf[3]);
-    *reinterpret_cast<uint2*>(gp + 3 * H) = pack4_bf16(go[0], go[1], go[2], go[3]);
+    const long long go_ = static_cast<long long>(r) * 4 * H + u;
+    store4_split(gates, gates_lo, go_ + 0 * H, gi);
+    store4_split(gates, gates_lo, go_ + 1 * H, gj);
+    store4_split(gates, gates_lo, go_ + 2 * H, gf);
+    store4_split(gates, gates_lo, go_ + 3 * H, go);
   }
 }
 
@@ -349,7 +378,8 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
                      const float* __restrict__ dc_in, long long ld_dc_in,
                      const int* __restrict__ seq_len, int t, int rows, int H,
                      __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dc_out,
-                     float* __restrict__ dh_pass_out, float* __restrict__ dbias) {
+                     float* __restrict__ dh_pass_out, float* __restrict__ dbias,
+                     const __nv_bfloat16* __restrict__ gates_lo, __nv_bfloat16* __restrict__ dz_lo) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL (see evc_ptx.cuh)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ float red[8][4][132];               // [row lane][gate][128 units + pad]
@@ -382,19 +412,22 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
       dc[0] = a.x; dc[1] = a.y; dc[2] = a.z; dc[3] = a.w;
     }
     __nv_bfloat16* zp = dz_out + static_cast<long long>(r) * 4 * H + u;
+    const long long zoff = static_cast<long long>(r) * 4 * H + u;
     if (!live) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
+      for (int g = 0; g < 4; ++g) {
+        *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
+        if (dz_lo != nullptr) *reinterpret_cast<uint2*>(dz_lo + zoff + g * H) = make_uint2(0u, 0u);
+      }
       *reinterpret_cast<float4*>(dc_out + off) = make_float4(dc[0], dc[1], dc[2], dc[3]);
       *reinterpret_cast<float4*>(dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
       continue;
     }
-    const __nv_bfloat16* gp = gates + static_cast<long long>(r) * 4 * H + u;
     float gi[4], gj[4], gf[4], go[4], cp[4] = {0.f, 0.f, 0.f, 0.f};
-    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 0 * H), gi);
-    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 1 * H), gj);
-    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 2 * H), gf);
-    unpack4_bf16(*reinterpret_cast<const uint2*>(gp + 3 * H), go);
+    load4_split(gates, gates_lo, zoff + 0 * H, gi);
+    load4_split(gates, gates_lo, zoff + 1 * H, gj);
+    load4_split(gates, gates_lo, zoff + 2 * H, gf);
+    load4_split(gates, gates_lo, zoff + 3 * H, go);
     if (c_prev != nullptr) {
       const float4 a = *reinterpret_cast<const float4*>(c_prev + off);
       cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w;
@@ -415,9 +448,17 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
     for (int g = 0; g < 4; ++g) {
       const uint2 packed = pack4_bf16(dz[g][0], dz[g][1], dz[g][2], dz[g][3]);
       *reinterpret_cast<uint2*>(zp + g * H) = packed;
-      // the bias gradient sums the values the weight-gradient GEMMs see: the bf16-rounded dz
+      // the bias gradient sums the values the weight-gradient GEMMs see: the bf16-rounded dz (+ its residual plane)
       float q[4];
       unpack4_bf16(packed, q);
+      if (dz_lo != nullptr) {
+        const uint2 pl = pack4_bf16(dz[g][0] - q[0], dz[g][1] - q[1], dz[g][2] - q[2], dz[g][3] - q[3]);
+        *reinterpret_cast<uint2*>(dz_lo + zoff + g * H) = pl;
+        float ql[4];
+        unpack4_bf16(pl, ql);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] += ql[k];
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) bsum[g][k] += q[k];
     }
@@ -440,13 +481,13 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
 
 // f32 [R,C] -> bf16 [R,ld] (columns C..ld-1 zero): bf16 operand copies of weights / activations
 __global__ void cast_bf16_kernel(const float* __restrict__ src, long long R, int C, int ld,
-                                 __nv_bfloat16* __restrict__ dst) {
+                                 __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo) {
   PDL_PROLOGUE();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= R * ld) return;
   const long long r = i / ld;
   const int c = static_cast<int>(i % ld);
-  dst[i] = (c < C) ? __float2bfloat16(src[r * C + c]) : __float2bfloat16(0.f);
+  store1_split(dst, dst_lo, i, (c < C) ? src[r * C + c] : 0.f);
 }
 
 // --------------------------------------------------------------------------------------
@@ -482,7 +523,7 @@ __global__ void moe_mix_fwd_kernel(const float* __restrict__ G, long long ldg, c
 __global__ void moe_mix_bwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
                                    long long lde, const float* __restrict__ dP, int V, int M,
                                    __nv_bfloat16* __restrict__ dG, long long lddg, __nv_bfloat16* __restrict__ dE,
-                                   long long ldde) {
+                                   long long ldde, __nv_bfloat16* __restrict__ dG_lo, __nv_bfloat16* __restrict__ dE_lo) {
   PDL_PROLOGUE();
   const int b = blockIdx.x;
   const float* g = G + b * ldg;
@@ -493,9 +534,9 @@ __global__ void moe_mix_bwd_kernel(const float* __restrict__ G, long long ldg, c
     const float dp = dP[static_cast<long long>(b) * V + c];
     for (int m = 0; m <= M; ++m) {
       const float s = (m < M) ? sig[m] : 0.f;
-      dG[b * lddg + c * (M + 1) + m] = __float2bfloat16(gate[m] * (s - pc) * dp);
+      store1_split(dG, dG_lo, b * lddg + c * (M + 1) + m, gate[m] * (s - pc) * dp);
     }
-    for (int m = 0; m < M; ++m) dE[b * ldde + c * M + m] = __float2bfloat16(gate[m] * sig[m] * (1.f - sig[m]) * dp);
+    for (int m = 0; m < M; ++m) store1_split(dE, dE_lo, b * ldde + c * M + m, gate[m] * sig[m] * (1.f - sig[m]) * dp);
   }
 }
 
@@ -558,7 +599,8 @@ __global__ void moe_mix_loss_kernel(const float* __restrict__ G, long long ldg, 
                                     const uint8_t* __restrict__ labels, int V, int M, float ce_scale,
                                     float kl_scale, float* __restrict__ P, float* __restrict__ ce_rows,
                                     float* __restrict__ kl_rows, __nv_bfloat16* __restrict__ dG, long long lddg,
-                                    __nv_bfloat16* __restrict__ dE, long long ldde) {
+                                    __nv_bfloat16* __restrict__ dE, long long ldde,
+                                    __nv_bfloat16* __restrict__ dG_lo, __nv_bfloat16* __restrict__ dE_lo) {
   PDL_PROLOGUE();
   __shared__ float sh[32];
   const int b = blockIdx.x;
@@ -596,9 +638,9 @@ __global__ void moe_mix_loss_kernel(const float* __restrict__ G, long long ldg, 
     }
     for (int m = 0; m <= M; ++m) {
       const float sgm = (m < M) ? sig[m] : 0.f;
-      dG[b * lddg + c * (M + 1) + m] = __float2bfloat16(gate[m] * (sgm - pc) * dp);
+      store1_split(dG, dG_lo, b * lddg + c * (M + 1) + m, gate[m] * (sgm - pc) * dp);
     }
-    for (int m = 0; m < M; ++m) dE[b * ldde + c * M + m] = __float2bfloat16(gate[m] * sig[m] * (1.f - sig[m]) * dp);
+    for (int m = 0; m < M; ++m) store1_split(dE, dE_lo, b * ldde + c * M + m, gate[m] * sig[m] * (1.f - sig[m]) * dp);
   }
   ce = block_sum(ce, sh);
   if (threadIdx.x == 0) ce_rows[b] = ce;
@@ -698,7 +740,8 @@ __global__ void sumsq_kernel(const float* __restrict__ g, const float* __restric
 __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n, const float* __restrict__ normsq, float clip,
                                  float wd, const float* __restrict__ lr_t, float b1, float b2, float eps,
-                                 __nv_bfloat16* __restrict__ shadow, int cols, long long ld_shadow) {
+                                 __nv_bfloat16* __restrict__ shadow, int cols, long long ld_shadow,
+                                 __nv_bfloat16* __restrict__ shadow_lo) {
   PDL_PROLOGUE();
   float scale = 1.f;
   if (clip > 0.f) {
@@ -728,11 +771,7 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
     *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
     *reinterpret_cast<float4*>(w + i) = make_float4(wa[0], wa[1], wa[2], wa[3]);
-    if (shadow) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(wa[0], wa[1]), hi = __floats2bfloat162_rn(wa[2], wa[3]);
-      *reinterpret_cast<uint2*>(shadow + (i / cols) * ld_shadow + (i % cols)) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    }
+    if (shadow) store4_split(shadow, shadow_lo, (i / cols) * ld_shadow + (i % cols), wa);
   }
 }
 
@@ -905,7 +944,7 @@ inline int grid_for(long long n, int block, int cap) {
 namespace evc {
 int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, const float* bias, const float* c_prev,
                          const void* h_prev, const int* seq_len, int t, int rows, int H, float* c_out, void* h_out,
-                         void* gates, cudaStream_t stream) {
+                         void* gates, cudaStream_t stream, const void* h_prev_lo, void* h_out_lo, void* gates_lo) {
   const long long n = static_cast<long long>(rows) * (H / 4);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
@@ -918,14 +957,17 @@ int launch_lstm_cell_fwd(const float* z_part, int S, long long part_stride, cons
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, lstm_cell_fwd_kernel, z_part, S, part_stride, bias, c_prev,
                      static_cast<const __nv_bfloat16*>(h_prev), seq_len, t, rows, H, c_out,
-                     static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(gates));
+                     static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(gates),
+                     static_cast<const __nv_bfloat16*>(h_prev_lo), static_cast<__nv_bfloat16*>(h_out_lo),
+                     static_cast<__nv_bfloat16*>(gates_lo));
   count_launch();
   return check_launch("lstm_cell_fwd");
 }
 int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, const void* gates, const float* c_prev,
                          const float* dh_ext, long long ld_dh_ext, const float* dh_pass_in, long long ld_dh_pass_in,
                          const float* dc_in, long long ld_dc_in, const int* seq_len, int t, int rows, int H,
-                         void* dz_out, float* dc_out, float* dh_pass_out, float* dbias, cudaStream_t stream) {
+                         void* dz_out, float* dc_out, float* dh_pass_out, float* dbias, cudaStream_t stream,
+                         const void* gates_lo, void* dz_lo) {
   if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_cell_bwd: H must be a multiple of 128");
   const int col_blocks = H / 128;
   int row_groups = (rows + 7) / 8;
@@ -942,14 +984,16 @@ int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, con
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, dh_part, S, part_stride, static_cast<const __nv_bfloat16*>(gates),
                      c_prev, dh_ext, ld_dh_ext, dh_pass_in, ld_dh_pass_in, dc_in, ld_dc_in, seq_len, t, rows, H,
-                     static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out, dbias);
+                     static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out, dbias,
+                     static_cast<const __nv_bfloat16*>(gates_lo), static_cast<__nv_bfloat16*>(dz_lo));
   count_launch();
   return check_launch("lstm_cell_bwd");
 }
 }  // namespace evc
 
 extern "C" int evc_frames_pack(const float* src, int B, int T, int D, const int* frame_idx, int idx_per_batch,
-                               int K, int num_chunks, int normalize, void* out_bf16, float* out_f32, void* stream) {
+                               int K, int num_chunks, int normalize, void* out_bf16, float* out_f32, void* out_lo,
+                               void* stream) {
   if (B <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "frames_pack: empty batch");
   if (D % 4 != 0) return set_error(EVC_ERR_ARG, "frames_pack: feature size must be a multiple of 4");
   if (num_chunks <= 0 || K % num_chunks != 0)
@@ -959,14 +1003,14 @@ extern "C" int evc_frames_pack(const float* src, int B, int T, int D, const int*
   const int grid = static_cast<int>((warps * 32 + block - 1) / block);
   pdl_launch(frames_pack_kernel, dim3(grid), dim3(block), 0, EVC_STREAM(stream), src, B, T, D, frame_idx, idx_per_batch, K, num_chunks,
                                                              normalize, static_cast<__nv_bfloat16*>(out_bf16),
-                                                             out_f32);
+                                                             out_f32, static_cast<__nv_bfloat16*>(out_lo));
   count_launch();
   return check_launch("frames_pack");
 }
 
 extern "C" int evc_frames_pack_u8(const unsigned char* src, const int* num_frames, int B, int T, int D,
                                   const int* frame_idx, int idx_per_batch, int K, int num_chunks, int normalize,
-                                  void* out_bf16, float* out_f32, void* stream) {
+                                  void* out_bf16, float* out_f32, void* out_lo, void* stream) {
   if (B <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "frames_pack_u8: empty batch");
   if (D % 4 != 0) return set_error(EVC_ERR_ARG, "frames_pack_u8: feature size must be a multiple of 4");
   if (num_frames == nullptr) return set_error(EVC_ERR_ARG, "frames_pack_u8: num_frames required (zero padding)");
@@ -977,7 +1021,8 @@ extern "C" int evc_frames_pack_u8(const unsigned char* src, const int* num_frame
   const int grid = static_cast<int>((warps * 32 + block - 1) / block);
   pdl_launch(frames_pack_u8_kernel, dim3(grid), dim3(block), 0, EVC_STREAM(stream), src, num_frames, B, T, D, frame_idx, idx_per_batch, K,
                                                                 num_chunks, normalize,
-                                                                static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+                                                                static_cast<__nv_bfloat16*>(out_bf16), out_f32,
+                                                                static_cast<__nv_bfloat16*>(out_lo));
   count_launch();
   return check_launch("frames_pack_u8");
 }
@@ -1029,20 +1074,24 @@ extern "C" int evc_random_uniform(unsigned long long seed, unsigned long long of
 }
 
 extern "C" int evc_state_pack(const float* c0, const void* h0, const float* c1, const void* h1, int rows, int H,
-                              void* out_bf16, float* out_f32, void* stream) {
+                              void* out_bf16, float* out_f32, const void* h0_lo, const void* h1_lo, void* out_lo,
+                              void* stream) {
+  if ((h0_lo == nullptr) != (h1_lo == nullptr)) return set_error(EVC_ERR_ARG, "state_pack: both h lo planes or none");
   const long long n = static_cast<long long>(rows) * H;
   pdl_launch(state_pack_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, EVC_STREAM(stream), 
       c0, static_cast<const __nv_bfloat16*>(h0), c1, static_cast<const __nv_bfloat16*>(h1), n, H,
-      static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+      static_cast<__nv_bfloat16*>(out_bf16), out_f32, static_cast<const __nv_bfloat16*>(h0_lo),
+      static_cast<const __nv_bfloat16*>(h1_lo), static_cast<__nv_bfloat16*>(out_lo));
   count_launch();
   return check_launch("state_pack");
 }
 
-extern "C" int evc_cast_bf16(const float* src, long long rows, int cols, int ld, void* dst, void* stream) {
+extern "C" int evc_cast_bf16(const float* src, long long rows, int cols, int ld, void* dst, void* dst_lo,
+                             void* stream) {
   if (ld < cols) return set_error(EVC_ERR_ARG, "cast_bf16: ld < cols");
   const long long n = rows * ld;
   pdl_launch(cast_bf16_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, EVC_STREAM(stream), 
-      src, rows, cols, ld, static_cast<__nv_bfloat16*>(dst));
+      src, rows, cols, ld, static_cast<__nv_bfloat16*>(dst), static_cast<__nv_bfloat16*>(dst_lo));
   count_launch();
   return check_launch("cast_bf16");
 }
@@ -1057,11 +1106,13 @@ extern "C" int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, lo
 }
 
 extern "C" int evc_moe_mix_bwd(const float* G, long long ldg, const float* E, long long lde, const float* dP, int B,
-                               int V, int M, void* dG, long long lddg, void* dE, long long ldde, void* stream) {
+                               int V, int M, void* dG, long long lddg, void* dE, long long ldde, void* dG_lo,
+                               void* dE_lo, void* stream) {
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix_bwd: 1 <= num_mixtures <= 8");
   if (B <= 0) return EVC_OK;
   pdl_launch(moe_mix_bwd_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, dP, V, M, static_cast<__nv_bfloat16*>(dG),
-                                                        lddg, static_cast<__nv_bfloat16*>(dE), ldde);
+                                                        lddg, static_cast<__nv_bfloat16*>(dE), ldde,
+                                                        static_cast<__nv_bfloat16*>(dG_lo), static_cast<__nv_bfloat16*>(dE_lo));
   count_launch();
   return check_launch("moe_mix_bwd");
 }
@@ -1079,12 +1130,13 @@ extern "C" int evc_ce_kl_loss(const float* P, const float* PT, const unsigned ch
 extern "C" int evc_moe_mix_loss(const float* G, long long ldg, const float* E, long long lde, const float* PT,
                                 const unsigned char* labels, int B, int V, int M, float ce_scale, float kl_scale,
                                 float* P, float* ce_rows, float* kl_rows, void* dG, long long lddg, void* dE,
-                                long long ldde, void* stream) {
+                                long long ldde, void* dG_lo, void* dE_lo, void* stream) {
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix_loss: 1 <= num_mixtures <= 8");
   if (labels == nullptr || ce_rows == nullptr) return set_error(EVC_ERR_ARG, "moe_mix_loss: labels and ce_rows required");
   if (B <= 0) return EVC_OK;
   pdl_launch(moe_mix_loss_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, PT, labels, V, M, ce_scale,
-             kl_scale, P, ce_rows, kl_rows, static_cast<__nv_bfloat16*>(dG), lddg, static_cast<__nv_bfloat16*>(dE), ldde);
+             kl_scale, P, ce_rows, kl_rows, static_cast<__nv_bfloat16*>(dG), lddg, static_cast<__nv_bfloat16*>(dE), ldde,
+             static_cast<__nv_bfloat16*>(dG_lo), static_cast<__nv_bfloat16*>(dE_lo));
   count_launch();
   return check_launch("moe_mix_loss");
 }
@@ -1137,7 +1189,8 @@ extern "C" int evc_sumsq(const float* g, const float* w, float weight_decay, lon
 
 extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
                              float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2,
-                             float eps, void* shadow_bf16, int cols, long long ld_shadow, void* stream) {
+                             float eps, void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo,
+                             void* stream) {
   if (shadow_bf16 && cols <= 0) return set_error(EVC_ERR_ARG, "clip_adam: cols required with a bf16 copy");
   if (n % 4 != 0 || (shadow_bf16 && (cols % 4 != 0 || ld_shadow % 4 != 0)) ||
       ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -1145,7 +1198,8 @@ extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long 
     return set_error(EVC_ERR_ARG, "clip_adam: tensors must be 16-byte aligned with sizes/cols multiple of 4");
   pdl_launch(clip_adam_kernel, dim3(grid_for(n / 4, 256, 148 * 8)), dim3(256), 0, EVC_STREAM(stream), 
       w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps,
-      static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow);
+      static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow,
+      static_cast<__nv_bfloat16*>(shadow_lo));
   count_launch();
   return check_launch("clip_adam");
 }

@@ -59,12 +59,16 @@ def overlap_mode() -> int:
 class _Layer:
     """Buffers of one BasicLSTMCell unrolled over T steps for `rows` sequences."""
 
-    def __init__(self, rows, H, T, training, dev):
+    def __init__(self, rows, H, T, training, dev, precise=False):
         self.rows, self.H, self.T = rows, H, T
         self.h_all = torch.zeros(T + 1, rows, H, dtype=BF16, device=dev)
         self.c_all = torch.zeros(T + 1, rows, H, dtype=torch.float32, device=dev)
         self.gates = torch.empty(T, rows, 4 * H, dtype=BF16, device=dev) if training else None
         self.dz = torch.empty(T, rows, 4 * H, dtype=BF16, device=dev) if training else None
+        # residual planes of the split-bf16 mode (None otherwise)
+        self.h_lo = torch.zeros(T + 1, rows, H, dtype=BF16, device=dev) if precise else None
+        self.gates_lo = torch.empty(T, rows, 4 * H, dtype=BF16, device=dev) if (precise and training) else None
+        self.dz_lo = torch.empty(T, rows, 4 * H, dtype=BF16, device=dev) if (precise and training) else None
 
 
 class HLstmEngine:
@@ -77,6 +81,7 @@ class HLstmEngine:
         self.B, self.K, self.C = batch, num_frames_in, num_chunks
         self.ell = num_frames_in // num_chunks
         self.training = training
+        self.precise = bool(getattr(params, "precise", False))
         self.overlap = overlap_mode()
         self._side: Optional[torch.cuda.Stream] = None
         self._events = []
@@ -84,27 +89,32 @@ class HLstmEngine:
         H, D, V, M, S = cfg.lstm_cells, cfg.feature_size, cfg.vocab_size, cfg.num_mixtures, cfg.state_size
         self.R1 = self.C * self.B
         B, R1, ell, C = self.B, self.R1, self.ell, self.C
+        px = self.precise
         self.x = torch.empty(ell, R1, D, dtype=BF16, device=dev)
+        self.x_lo = torch.empty(ell, R1, D, dtype=BF16, device=dev) if px else None
         self.len_l1 = torch.zeros(R1, dtype=torch.int32, device=dev)
         self.len_l2 = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.l1 = [_Layer(R1, H, ell, training, dev) for _ in range(2)]
+        self.l1 = [_Layer(R1, H, ell, training, dev, px) for _ in range(2)]
         self.l2_in = torch.empty(C, B, S, dtype=BF16, device=dev)
-        self.l2 = [_Layer(B, H, C, training, dev) for _ in range(2)]
+        self.l2_in_lo = torch.empty(C, B, S, dtype=BF16, device=dev) if px else None
+        self.l2 = [_Layer(B, H, C, training, dev, px) for _ in range(2)]
         self.state = torch.empty(B, S, dtype=torch.float32, device=dev)
         self.state_bf16 = torch.empty(B, S, dtype=BF16, device=dev)
+        self.state_lo = torch.empty(B, S, dtype=BF16, device=dev) if px else None
         self.ldg, self.lde = V * (M + 1), V * M
         self.G = torch.empty(B, self.ldg, dtype=torch.float32, device=dev)
         self.E = torch.empty(B, self.lde, dtype=torch.float32, device=dev)
         self.pred = torch.empty(B, V, dtype=torch.float32, device=dev)
         # split-K partial slabs of the recurrence steps (one scratch buffer shared by all cells)
-        ws = max(ops.lstm_workspace_bytes(R1, H, D), ops.lstm_workspace_bytes(R1, H, H),
-                 ops.lstm_workspace_bytes(B, H, S), ops.lstm_workspace_bytes(B, H, H))
+        ws = max(ops.lstm_workspace_bytes(R1, H, D, px), ops.lstm_workspace_bytes(R1, H, H, px),
+                 ops.lstm_workspace_bytes(B, H, S, px), ops.lstm_workspace_bytes(B, H, H, px))
         self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
         self.workspace2 = (torch.empty(ops.lstm_workspace_bytes(B, H, H), dtype=torch.uint8, device=dev)
                            if self.overlap & OVERLAP_CELLS_L2 else None)
         # scratch of the resident-weights persistent recurrence (hoisted input projection Zx, slice layout of Wh,
         # step flags) for the cells whose row count is eligible: RNN_L2 always, RNN_L1 up to ~2048 rows
-        rec = max(ops.lstm_rec_workspace_bytes(R1, H, ell), ops.lstm_rec_workspace_bytes(B, H, C)) if resident_mode() else 0
+        rec = (max(ops.lstm_rec_workspace_bytes(R1, H, ell), ops.lstm_rec_workspace_bytes(B, H, C))
+               if resident_mode() and not px else 0)
         self.rec_ws = None
         if rec:
             raw = torch.empty(rec + 1024, dtype=torch.uint8, device=dev)
@@ -114,6 +124,8 @@ class HLstmEngine:
             self.lddg, self.ldde = ops.pad8(self.ldg, 64), ops.pad8(self.lde, 64)
             self.dG = torch.zeros(B, self.lddg, dtype=BF16, device=dev)
             self.dE = torch.zeros(B, self.ldde, dtype=BF16, device=dev)
+            self.dG_lo = torch.zeros(B, self.lddg, dtype=BF16, device=dev) if px else None
+            self.dE_lo = torch.zeros(B, self.ldde, dtype=BF16, device=dev) if px else None
             self.dP = torch.empty(B, V, dtype=torch.float32, device=dev)
             self.dstate = torch.zeros(B, S, dtype=torch.float32, device=dev)
             self.dx_l2 = torch.empty(C * B, H, dtype=torch.float32, device=dev)       # d h0 sequence of RNN_L2
@@ -136,8 +148,16 @@ class HLstmEngine:
         return self._events[i]
 
     def _cell_fwd(self, layer: _Layer, x, x_stride, Kx, level, cell, seq_len, t_begin=0, t_end=None,
-                  cuda_stream=None, workspace=None):
+                  cuda_stream=None, workspace=None, x_lo=None):
         p = self.p
+        if self.precise:
+            # split-bf16 mode: every step = 3-segment split-K GEMM into f32 slabs + the cell kernel
+            k = p.kernel(level, cell)
+            ops.lstm_seq_fwd(x, x_stride, Kx, p.shadow[k], p.w[p.bias(level, cell)], layer.rows, layer.H, layer.T,
+                             seq_len, layer.h_all, layer.c_all, layer.gates, self.workspace, t_begin, t_end,
+                             cuda_stream, x_lo=x_lo, W_lo=p.shadow_lo[k], h_lo_all=layer.h_lo,
+                             gates_lo_all=layer.gates_lo)
+            return
         if (t_begin == 0 and t_end is None and cuda_stream is None and self._resident_ok(layer)
                 and x_stride == layer.rows * Kx):
             dev, cur = p.device, torch.cuda.current_stream()
@@ -203,11 +223,22 @@ class HLstmEngine:
             # quantised tfrecord features: Dequantize + zero padding fused into the pack kernel
             if raw_num_frames is None:
                 raise ValueError("uint8 features need the unsampled num_frames (int32) for zero padding")
-            ops.frames_pack_u8(src, raw_num_frames, frame_idx, self.K, C, normalize, out_bf16=self.x)
+            ops.frames_pack_u8(src, raw_num_frames, frame_idx, self.K, C, normalize, out_bf16=self.x, out_lo=self.x_lo)
         else:
-            ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x)
+            ops.frames_pack(src, frame_idx, self.K, C, normalize, out_bf16=self.x, out_lo=self.x_lo)
         ops.lstm_lengths(num_frames, C, ell, self.len_l1, self.len_l2)
         a, b = self.l1
+        if self.precise:
+            self._cell_fwd(a, self.x, R1 * D, D, 0, 0, self.len_l1, x_lo=self.x_lo)
+            self._cell_fwd(b, a.h_all[1:], R1 * H, H, 0, 1, self.len_l1, x_lo=a.h_lo[1:])
+            ops.state_pack(a.c_all[ell], a.h_all[ell], b.c_all[ell], b.h_all[ell], R1, H, out_bf16=self.l2_in,
+                           h0_lo=a.h_lo[ell], h1_lo=b.h_lo[ell], out_lo=self.l2_in_lo)
+            a2, b2 = self.l2
+            self._cell_fwd(a2, self.l2_in, B * S, S, 1, 0, self.len_l2, x_lo=self.l2_in_lo)
+            self._cell_fwd(b2, a2.h_all[1:], B * H, H, 1, 1, self.len_l2, x_lo=a2.h_lo[1:])
+            ops.state_pack(a2.c_all[C], a2.h_all[C], b2.c_all[C], b2.h_all[C], B, H, out_bf16=self.state_bf16,
+                           out_f32=self.state, h0_lo=a2.h_lo[C], h1_lo=b2.h_lo[C], out_lo=self.state_lo)
+            return
         if (self.overlap & OVERLAP_CELLS) and R1 > 1024 and not self._resident_ok(a):
             # MultiRNNCell wavefront: cell 1 step t next to cell 0 step t+1 (fused-epilogue steps only: the
             # split-K path of the small-row steps shares one scratch buffer)
@@ -230,9 +261,11 @@ class HLstmEngine:
         the two logit GEMMs (the training step applies the mixture inside its fused loss kernel)."""
         p, cfg = self.p, self.cfg
         S, V, M = cfg.state_size, cfg.vocab_size, cfg.num_mixtures
-        ops.gemm(self.state_bf16, p.shadow[p.gates_w], self.B, self.ldg, S, self.G, b_mn=True)
+        lo = p.shadow_lo.get if self.precise else (lambda n: None)
+        ops.gemm(self.state_bf16, p.shadow[p.gates_w], self.B, self.ldg, S, self.G, b_mn=True,
+                 A_lo=self.state_lo, B_lo=lo(p.gates_w))
         ops.gemm(self.state_bf16, p.shadow[p.experts_w], self.B, self.lde, S, self.E, b_mn=True,
-                 bias=p.w[p.experts_b])
+                 bias=p.w[p.experts_b], A_lo=self.state_lo, B_lo=lo(p.experts_w))
         if mix:
             ops.moe_mix_fwd(self.G, self.ldg, self.E, self.lde, self.B, V, M, self.pred)
 
@@ -242,7 +275,7 @@ class HLstmEngine:
         cfg = self.cfg
         ops.moe_mix_loss(self.G, self.ldg, self.E, self.lde, teacher_pred, labels_u8, self.B, cfg.vocab_size,
                          cfg.num_mixtures, ce_scale, kl_scale, self.pred, ce_rows, kl_rows, self.dG, self.lddg,
-                         self.dE, self.ldde)
+                         self.dE, self.ldde, self.dG_lo, self.dE_lo)
 
     # ------------------------------------------------------------------ backward
     def _cell_bwd(self, layer: _Layer, level, cell, Kx, seq_len, dh_ext, dfinal, col, scratch):
@@ -254,22 +287,29 @@ class HLstmEngine:
         # (the bias gradient -- column sums of dz -- is accumulated by the cell kernel while it writes dz)
         ops.lstm_seq_bwd(p.shadow[p.kernel(level, cell)], Kx, layer.rows, H, layer.T, seq_len, layer.gates,
                          layer.c_all, dh_ext, dfinal[:, col + H:], ld, dfinal[:, col:], ld,
-                         scratch[0], scratch[1], layer.dz, self.workspace, dbias=p.g[p.bias(level, cell)])
+                         scratch[0], scratch[1], layer.dz, self.workspace, dbias=p.g[p.bias(level, cell)],
+                         W_lo=p.shadow_lo.get(p.kernel(level, cell)), gates_lo_all=layer.gates_lo,
+                         dz_lo_all=layer.dz_lo)
 
-    def _cell_wgrad(self, layer: _Layer, level, cell, x2d, Kx):
+    def _cell_wgrad(self, layer: _Layer, level, cell, x2d, Kx, x2d_lo=None):
         """dW = [x | h_prev]^T dz over all steps and rows (db comes from the backward recurrence, _cell_bwd)."""
         p = self.p
         H, R = layer.H, layer.T * layer.rows
         dz = layer.dz.view(R, 4 * H)
+        dz_lo = layer.dz_lo.view(R, 4 * H) if self.precise else None
+        h_lo = layer.h_lo.view(-1, H) if self.precise else None
         gW = p.g[p.kernel(level, cell)]
-        ops.gemm(x2d, dz, Kx, 4 * H, R, gW[:Kx], a_mn=True, b_mn=True, lda=Kx, ldc=4 * H)
-        ops.gemm(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], a_mn=True, b_mn=True, lda=H, ldc=4 * H)
+        ops.gemm(x2d, dz, Kx, 4 * H, R, gW[:Kx], a_mn=True, b_mn=True, lda=Kx, ldc=4 * H, A_lo=x2d_lo, B_lo=dz_lo)
+        ops.gemm(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], a_mn=True, b_mn=True, lda=H, ldc=4 * H,
+                 A_lo=h_lo, B_lo=dz_lo)
 
     def _cell_dx(self, layer: _Layer, level, cell, Kx, out):
         """d input sequence = dz @ Wx^T  (Wx = first Kx rows of the kernel)."""
         p = self.p
         H, R = layer.H, layer.T * layer.rows
-        ops.gemm(layer.dz.view(R, 4 * H), p.shadow[p.kernel(level, cell)], R, Kx, 4 * H, out, ldb=4 * H)
+        ops.gemm(layer.dz.view(R, 4 * H), p.shadow[p.kernel(level, cell)], R, Kx, 4 * H, out, ldb=4 * H,
+                 A_lo=layer.dz_lo.view(R, 4 * H) if self.precise else None,
+                 B_lo=p.shadow_lo.get(p.kernel(level, cell)))
 
     def backward(self, dP: torch.Tensor, dstate_preset: bool = False) -> None:
         """Gradients of every weight into params.g given dP = dLoss/dpredictions [B,V].
@@ -285,16 +325,24 @@ class HLstmEngine:
         p, cfg = self.p, self.cfg
         S, V, M, B = cfg.state_size, cfg.vocab_size, cfg.num_mixtures, self.B
         if not logits_done:
-            ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde)
+            ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde,
+                            self.dG_lo, self.dE_lo)
         if not dstate_preset:
             ops.fill_f32(self.dstate, 0.0)
-        ops.gemm(self.dG, p.shadow[p.gates_w], B, S, self.ldg, self.dstate, split_k=8, accumulate=True)
-        ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=8, accumulate=True)
-        ops.gemm(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], a_mn=True, b_mn=True)
-        ops.gemm(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], a_mn=True, b_mn=True)
+        lo = p.shadow_lo.get if self.precise else (lambda n: None)
+        ops.gemm(self.dG, p.shadow[p.gates_w], B, S, self.ldg, self.dstate, split_k=8, accumulate=True,
+                 A_lo=self.dG_lo, B_lo=lo(p.gates_w))
+        ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=8, accumulate=True,
+                 A_lo=self.dE_lo, B_lo=lo(p.experts_w))
+        ops.gemm(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], a_mn=True, b_mn=True,
+                 A_lo=self.state_lo, B_lo=self.dG_lo)
+        ops.gemm(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], a_mn=True, b_mn=True,
+                 A_lo=self.state_lo, B_lo=self.dE_lo)
         gbe = p.g[p.experts_b]
         ops.fill_f32(gbe, 0.0)
         ops.colsum_bf16(self.dE, B, self.lde, self.ldde, gbe)
+        if self.precise:
+            ops.colsum_bf16(self.dE_lo, B, self.lde, self.ldde, gbe)      # accumulates: hi + lo
 
     def lstm_backward(self) -> None:
         """Backward of both LSTM levels given self.dstate = dLoss/d(final state)."""
@@ -323,16 +371,17 @@ class HLstmEngine:
                 self._cell_wgrad(*args)
         # ---- RNN_L2 (cell 1 first: its input gradient feeds cell 0)
         self._cell_bwd(b2, 1, 1, H, self.len_l2, None, self.dstate, 2 * H, self.scr_l2)
-        wgrad_aside(0, b2, 1, 1, a2.h_all[1:].view(-1, H), H)
+        px = self.precise
+        wgrad_aside(0, b2, 1, 1, a2.h_all[1:].view(-1, H), H, a2.h_lo[1:].view(-1, H) if px else None)
         self._cell_dx(b2, 1, 1, H, self.dx_l2)
         self._cell_bwd(a2, 1, 0, S, self.len_l2, self.dx_l2, self.dstate, 0, self.scr_l2)
-        wgrad_aside(1, a2, 1, 0, self.l2_in.view(-1, S), S)
+        wgrad_aside(1, a2, 1, 0, self.l2_in.view(-1, S), S, self.l2_in_lo.view(-1, S) if px else None)
         self._cell_dx(a2, 1, 0, S, self.dl2_in)
         # ---- RNN_L1: final-state gradient of chunk i = gradient of RNN_L2's input at step i
         self._cell_bwd(b, 0, 1, H, self.len_l1, None, self.dl2_in, 2 * H, self.scr_l1)
-        wgrad_aside(2, b, 0, 1, a.h_all[1:].view(-1, H), H)
+        wgrad_aside(2, b, 0, 1, a.h_all[1:].view(-1, H), H, a.h_lo[1:].view(-1, H) if px else None)
         self._cell_dx(b, 0, 1, H, self.dx_l1)
         self._cell_bwd(a, 0, 0, D, self.len_l1, self.dx_l1, self.dl2_in, 0, self.scr_l1)
-        self._cell_wgrad(a, 0, 0, self.x.view(-1, D), D)
+        self._cell_wgrad(a, 0, 0, self.x.view(-1, D), D, self.x_lo.view(-1, D) if px else None)
         if side is not None:
             main.wait_stream(side)

@@ -3,7 +3,7 @@ frame_level_models.py:15-47,218-219,237-238,286-289; video_level_models.py:13-19
 train.py:27-99, eval_finetune.py:21-60).  Same names; defaults are the reference's except where every run_*.sh
 overrides them (`lstm_layers` 2 instead of 1, `feature_names`/`feature_sizes` "rgb, audio"/"1024, 128" instead of
 "rgb"/"1024", `frame_features` True): the defaults here are the run_*.sh configuration.  Set them as attributes or
-via ``parse``.  `sampling` and `output_dir` are additions (BASELINE config #5; the converter's target directory)."""
+via ``parse``.  `sampling`, `precise` and `output_dir` are additions (BASELINE config #5; the converter's target directory)."""
 from __future__ import annotations
 
 
@@ -85,4 +85,5 @@ FLAGS.define("gpu", 0, "GPU on which the code will run (single-process runs; tor
 FLAGS.define("run_once", False, "Whether to run eval only once.")
 FLAGS.define("log_device_placement", False, "accepted for command-line parity, unused")
 FLAGS.define("sampling", "uniform", "student frame sampler: uniform | random_frames | random_sequence")
+FLAGS.define("precise", False, "split-bf16 operands (3 tensor-core products per contraction) instead of plain bf16")
 FLAGS.define("output_dir", "", "train_convert_model: where the student-only checkpoint goes")

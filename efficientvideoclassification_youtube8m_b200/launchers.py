@@ -179,7 +179,8 @@ class Trainer:
         kw = dict(batch_size=FLAGS.batch_size, device=device, every_n=FLAGS.every_n,
                   base_learning_rate=FLAGS.base_learning_rate, clip_gradient_norm=FLAGS.clip_gradient_norm,
                   regularization_penalty=FLAGS.regularization_penalty, learning_rate_decay=FLAGS.learning_rate_decay,
-                  learning_rate_decay_examples=FLAGS.learning_rate_decay_examples, sampling=FLAGS.sampling)
+                  learning_rate_decay_examples=FLAGS.learning_rate_decay_examples, sampling=FLAGS.sampling,
+                  precise=FLAGS.precise)
         if finetune:
             self.step_fn = StudentFinetuneTrainer(cfg, **kw)
             self.param_sets = [self.step_fn.student]
@@ -267,10 +268,10 @@ def _evaluate(argv, both: bool):
         raise IOError("'eval_data_pattern' was not specified. Nothing to evaluate.")
     reader = _reader()
     cfg = _model_config(reader)
-    student = HLstmParams("model_student", cfg, dev, seed=None)
+    student = HLstmParams("model_student", cfg, dev, seed=None, precise=FLAGS.precise)
     sets = [student]
     if both:
-        teacher = HLstmParams("model", cfg, dev, seed=None)
+        teacher = HLstmParams("model", cfg, dev, seed=None, precise=FLAGS.precise)
         sets = [teacher, student]
         ev = TeacherStudentEvaluator(teacher, student, FLAGS.batch_size, FLAGS.every_n, FLAGS.num_inputs_to_lstm,
                                      top_k=FLAGS.top_k, sampling=FLAGS.sampling)

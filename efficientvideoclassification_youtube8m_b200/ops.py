@@ -31,33 +31,39 @@ def pad8(n: int, mult: int = 64) -> int:
 
 
 def gemm(A, B, M, N, K, out, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, bias=None,
-         split_k=1, accumulate=False):
-    """out[M,N] (=|+=) A[M,K] @ B[K,N]; see evc_gemm_bf16 for the storage conventions."""
+         split_k=1, accumulate=False, A_lo=None, B_lo=None):
+    """out[M,N] (=|+=) A[M,K] @ B[K,N]; see evc_gemm_bf16 for the storage conventions.  A_lo / B_lo: residual
+    planes of the split-bf16 mode (same layout as A / B; both or none)."""
     lda = lda if lda is not None else A.stride(0)
     ldb = ldb if ldb is not None else B.stride(0)
     ldc = ldc if ldc is not None else out.stride(0)
+    if A_lo is not None or B_lo is not None:
+        check(lib.evc_gemm_bf16x2(ptr(A), ptr(A_lo), int(a_mn), lda, ptr(B), ptr(B_lo), int(b_mn), ldb, M, N, K,
+                                  ptr(out), int(out.dtype == BF16), ldc, ptr(bias), split_k, int(accumulate), stream()),
+              "evc_gemm_bf16x2")
+        return out
     check(lib.evc_gemm_bf16(ptr(A), int(a_mn), lda, ptr(B), int(b_mn), ldb, M, N, K, ptr(out),
                             int(out.dtype == BF16), ldc, ptr(bias), split_k, int(accumulate), stream()),
           "evc_gemm_bf16")
     return out
 
 
-def frames_pack(src, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None):
-    _cuda(src, frame_idx, out_bf16, out_f32)
+def frames_pack(src, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None, out_lo=None):
+    _cuda(src, frame_idx, out_bf16, out_f32, out_lo)
     B, T, D = src.shape
     per_batch = int(frame_idx is not None and frame_idx.dim() == 2)
     check(lib.evc_frames_pack(ptr(src), B, T, D, ptr(frame_idx), per_batch, K, num_chunks, int(normalize),
-                              ptr(out_bf16), ptr(out_f32), stream()), "evc_frames_pack")
+                              ptr(out_bf16), ptr(out_f32), ptr(out_lo), stream()), "evc_frames_pack")
 
 
-def frames_pack_u8(src_u8, num_frames, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None):
+def frames_pack_u8(src_u8, num_frames, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None, out_lo=None):
     """frames_pack on the quantised (uint8) features: Dequantize + zero padding fused in."""
-    _cuda(src_u8, num_frames, frame_idx, out_bf16, out_f32)
+    _cuda(src_u8, num_frames, frame_idx, out_bf16, out_f32, out_lo)
     assert src_u8.dtype == torch.uint8 and num_frames.dtype == torch.int32
     B, T, D = src_u8.shape
     per_batch = int(frame_idx is not None and frame_idx.dim() == 2)
     check(lib.evc_frames_pack_u8(ptr(src_u8), ptr(num_frames), B, T, D, ptr(frame_idx), per_batch, K, num_chunks,
-                                 int(normalize), ptr(out_bf16), ptr(out_f32), stream()), "evc_frames_pack_u8")
+                                 int(normalize), ptr(out_bf16), ptr(out_f32), ptr(out_lo), stream()), "evc_frames_pack_u8")
 
 
 def num_frames_student(num_frames, every_n, max_frames=300, out=None):
@@ -115,18 +121,19 @@ def random_uniform(out, seed: int, offset: int = 0):
     return out
 
 
-def lstm_workspace_bytes(rows, H, Kx):
-    return int(lib.evc_lstm_workspace_bytes(rows, H, Kx))
+def lstm_workspace_bytes(rows, H, Kx, precise=False):
+    return int(lib.evc_lstm_workspace_bytes(rows, H, Kx, int(precise)))
 
 
 def lstm_seq_fwd(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_all, c_all, gates_all, workspace=None,
-                 t_begin=0, t_end=None, cuda_stream=None):
+                 t_begin=0, t_end=None, cuda_stream=None, x_lo=None, W_lo=None, h_lo_all=None, gates_lo_all=None):
     """All T steps of one BasicLSTMCell layer, or only steps [t_begin, t_end); on the current stream or on
-    the raw `cuda_stream` handle."""
+    the raw `cuda_stream` handle.  *_lo: residual planes of the split-bf16 mode."""
     t_end = T if t_end is None else t_end
     check(lib.evc_lstm_seq_fwd_steps(ptr(x), x_step_stride, Kx, ptr(W), ptr(bias), rows, H, T, t_begin, t_end,
                                      ptr(seq_len), ptr(h_all), ptr(c_all), ptr(gates_all), ptr(workspace),
                                      workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                                     ptr(x_lo), ptr(W_lo), ptr(h_lo_all), ptr(gates_lo_all),
                                      stream() if cuda_stream is None else cuda_stream), "evc_lstm_seq_fwd_steps")
 
 
@@ -143,21 +150,22 @@ def lstm_seq_fwd_resident(x, x_step_stride, Kx, W, bias, rows, H, T, seq_len, h_
 
 
 def lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates_all, c_all, dh_ext_all, dh_final, ld_dh_final, dc_final,
-                 ld_dc_final, dh_pass, dc, dz_all, workspace=None, dbias=None):
+                 ld_dc_final, dh_pass, dc, dz_all, workspace=None, dbias=None, W_lo=None, gates_lo_all=None,
+                 dz_lo_all=None):
     check(lib.evc_lstm_seq_bwd(ptr(W), Kx, rows, H, T, ptr(seq_len), ptr(gates_all), ptr(c_all), ptr(dh_ext_all),
                                ptr(dh_final), ld_dh_final, ptr(dc_final), ld_dc_final, ptr(dh_pass), ptr(dc),
                                ptr(dz_all), ptr(dbias), ptr(workspace),
                                workspace.numel() * workspace.element_size() if workspace is not None else 0,
-                               stream()), "evc_lstm_seq_bwd")
+                               ptr(W_lo), ptr(gates_lo_all), ptr(dz_lo_all), stream()), "evc_lstm_seq_bwd")
 
 
-def state_pack(c0, h0, c1, h1, rows, H, out_bf16=None, out_f32=None):
-    check(lib.evc_state_pack(ptr(c0), ptr(h0), ptr(c1), ptr(h1), rows, H, ptr(out_bf16), ptr(out_f32), stream()),
-          "evc_state_pack")
+def state_pack(c0, h0, c1, h1, rows, H, out_bf16=None, out_f32=None, h0_lo=None, h1_lo=None, out_lo=None):
+    check(lib.evc_state_pack(ptr(c0), ptr(h0), ptr(c1), ptr(h1), rows, H, ptr(out_bf16), ptr(out_f32), ptr(h0_lo),
+                             ptr(h1_lo), ptr(out_lo), stream()), "evc_state_pack")
 
 
-def cast_bf16(src, dst, rows, cols, ld):
-    check(lib.evc_cast_bf16(ptr(src), rows, cols, ld, ptr(dst), stream()), "evc_cast_bf16")
+def cast_bf16(src, dst, rows, cols, ld, dst_lo=None):
+    check(lib.evc_cast_bf16(ptr(src), rows, cols, ld, ptr(dst), ptr(dst_lo), stream()), "evc_cast_bf16")
 
 
 def fill_f32(t, value=0.0):
@@ -168,9 +176,9 @@ def moe_mix_fwd(G, ldg, E, lde, B, V, M, p_out):
     check(lib.evc_moe_mix_fwd(ptr(G), ldg, ptr(E), lde, B, V, M, ptr(p_out), stream()), "evc_moe_mix_fwd")
 
 
-def moe_mix_bwd(G, ldg, E, lde, dP, B, V, M, dG, lddg, dE, ldde):
-    check(lib.evc_moe_mix_bwd(ptr(G), ldg, ptr(E), lde, ptr(dP), B, V, M, ptr(dG), lddg, ptr(dE), ldde, stream()),
-          "evc_moe_mix_bwd")
+def moe_mix_bwd(G, ldg, E, lde, dP, B, V, M, dG, lddg, dE, ldde, dG_lo=None, dE_lo=None):
+    check(lib.evc_moe_mix_bwd(ptr(G), ldg, ptr(E), lde, ptr(dP), B, V, M, ptr(dG), lddg, ptr(dE), ldde, ptr(dG_lo),
+                              ptr(dE_lo), stream()), "evc_moe_mix_bwd")
 
 
 def ce_kl_loss(P, PT, labels, ce_scale, kl_scale, ce_rows, kl_rows, dP):
@@ -179,9 +187,11 @@ def ce_kl_loss(P, PT, labels, ce_scale, kl_scale, ce_rows, kl_rows, dP):
                              ptr(dP), stream()), "evc_ce_kl_loss")
 
 
-def moe_mix_loss(G, ldg, E, lde, PT, labels, B, V, M, ce_scale, kl_scale, P, ce_rows, kl_rows, dG, lddg, dE, ldde):
+def moe_mix_loss(G, ldg, E, lde, PT, labels, B, V, M, ce_scale, kl_scale, P, ce_rows, kl_rows, dG, lddg, dE, ldde,
+                 dG_lo=None, dE_lo=None):
     check(lib.evc_moe_mix_loss(ptr(G), ldg, ptr(E), lde, ptr(PT), ptr(labels), B, V, M, ce_scale, kl_scale, ptr(P),
-                               ptr(ce_rows), ptr(kl_rows), ptr(dG), lddg, ptr(dE), ldde, stream()), "evc_moe_mix_loss")
+                               ptr(ce_rows), ptr(kl_rows), ptr(dG), lddg, ptr(dE), ldde, ptr(dG_lo), ptr(dE_lo),
+                               stream()), "evc_moe_mix_loss")
 
 
 def reduce_rows(rows, scale, out):
@@ -207,9 +217,10 @@ def sumsq(g, w, weight_decay, out, out_wsq=None):
 
 
 def clip_adam(w, g, m, v, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps, shadow=None, cols=0,
-              ld_shadow=0):
+              ld_shadow=0, shadow_lo=None):
     check(lib.evc_clip_adam(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(normsq), clip_norm, weight_decay,
-                            ptr(lr_t), beta1, beta2, eps, ptr(shadow), cols, ld_shadow, stream()), "evc_clip_adam")
+                            ptr(lr_t), beta1, beta2, eps, ptr(shadow), cols, ld_shadow, ptr(shadow_lo), stream()),
+          "evc_clip_adam")
 
 
 def topk(P, k, labels=None):

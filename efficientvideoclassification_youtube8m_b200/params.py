@@ -59,8 +59,11 @@ class HLstmParams:
     """Weights, gradients, Adam state and bf16 operand copies of one variable scope."""
 
     def __init__(self, scope: str, cfg: ModelConfig, device, seed: Optional[int] = 0,
-                 lstm_gain: float = 1.0):
+                 lstm_gain: float = 1.0, precise: bool = False):
         self.scope, self.cfg, self.device = scope, cfg, torch.device(device)
+        # split-bf16 "precise" mode (include/evc.h): every operand copy gets a residual plane, contractions run
+        # as hi*hi + hi*lo + lo*hi (the mode in which the 200-step loss criterion holds at lr 1e-3)
+        self.precise = bool(precise)
         self.names = variable_names(scope)
         self.shapes = variable_shapes(scope, cfg)
         self.offsets, off = {}, 0
@@ -83,13 +86,15 @@ class HLstmParams:
             self.m[n] = self.flat_m[o:o + k].view(shp)
             self.v[n] = self.flat_v[o:o + k].view(shp)
         # bf16 operand copies (matrices only), row pitch padded to a multiple of 64
-        self.shadow, self.ld = {}, {}
+        self.shadow, self.ld, self.shadow_lo = {}, {}, {}
         for n in self.names:
             shp = self.shapes[n]
             if len(shp) == 2:
                 ld = ops.pad8(shp[1], 64)
                 self.ld[n] = ld
                 self.shadow[n] = torch.zeros(shp[0], ld, dtype=torch.bfloat16, device=self.device)
+                if self.precise:
+                    self.shadow_lo[n] = torch.zeros(shp[0], ld, dtype=torch.bfloat16, device=self.device)
         self.normsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
         self.wsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
         self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -193,7 +198,7 @@ class HLstmParams:
     def refresh_shadows(self) -> None:
         for n, s in self.shadow.items():
             rows, cols = self.shapes[n]
-            ops.cast_bf16(self.w[n], s, rows, cols, self.ld[n])
+            ops.cast_bf16(self.w[n], s, rows, cols, self.ld[n], self.shadow_lo.get(n))
 
     # ---- data-parallel optimizer sharding (ZeRO-1 style): every matrix is split into `world` row blocks; a
     # rank receives the averaged gradient of its block (reduce-scatter), updates only those rows of the f32
@@ -245,9 +250,13 @@ class HLstmParams:
                 cols, ld = self.shapes[n][1], self.ld[n]
                 ops.clip_adam(self.w[n][r0:r1], self.g[n][r0:r1], self.m[n][r0:r1], self.v[n][r0:r1],
                               self.normsq[i:i + 1], float(clip_gradient_norm), wd if n in reg else 0.0, self.lr_t,
-                              beta1, beta2, eps, self.shadow[n][r0:r1], cols, ld)
+                              beta1, beta2, eps, self.shadow[n][r0:r1], cols, ld,
+                              self.shadow_lo[n][r0:r1] if self.precise else None)
                 handles.append(dist.all_gather_into_tensor(self.shadow[n], self.shadow[n][r0:r1], group=group,
                                                            async_op=True))
+                if self.precise:
+                    handles.append(dist.all_gather_into_tensor(self.shadow_lo[n], self.shadow_lo[n][r0:r1],
+                                                               group=group, async_op=True))
             else:
                 ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],
                               float(clip_gradient_norm), 0.0, self.lr_t, beta1, beta2, eps, None, 0, 0)
@@ -313,4 +322,4 @@ class HLstmParams:
             cols = self.shapes[n][1] if shadow is not None else 0
             ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],
                           float(clip_gradient_norm), wd if n in reg else 0.0, self.lr_t, beta1, beta2, eps,
-                          shadow, cols, self.ld.get(n, 0))
+                          shadow, cols, self.ld.get(n, 0), self.shadow_lo.get(n))

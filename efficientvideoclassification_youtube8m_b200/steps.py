@@ -232,12 +232,14 @@ class TeacherStudentTrainer(_Base):
                  regularization_penalty: float = 2.0, teacher_seed: Optional[int] = 0,
                  student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None,
                  learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0,
-                 sampling: str = "uniform", sampling_seed: int = 0):
+                 sampling: str = "uniform", sampling_seed: int = 0, precise: bool = False):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
                          clip_gradient_norm, regularization_penalty, shard_optimizer, learning_rate_decay,
                          learning_rate_decay_examples, sampling, sampling_seed)
-        self.teacher = HLstmParams("model", cfg, device, teacher_seed, lstm_gain)
-        self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
+        # precise: split-bf16 operands (hi + lo planes, 3 tensor-core products per contraction): the arithmetic in
+        # which the training curve follows the float32 reference graph to 1 % over hundreds of steps (include/evc.h)
+        self.teacher = HLstmParams("model", cfg, device, teacher_seed, lstm_gain, precise)
+        self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain, precise)
         self.t_eng = HLstmEngine(self.teacher, batch_size, MAX_FRAMES, num_inputs_to_lstm, training=True)
         self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
         dev, B = self.device, batch_size
@@ -377,11 +379,11 @@ class StudentFinetuneTrainer(_Base):
                  clip_gradient_norm: float = 1.0, regularization_penalty: float = 2.0,
                  student_seed: Optional[int] = 1, lstm_gain: float = 1.0, shard_optimizer: Optional[bool] = None,
                  learning_rate_decay: float = 1.0, learning_rate_decay_examples: float = 4000000.0,
-                 sampling: str = "uniform", sampling_seed: int = 0):
+                 sampling: str = "uniform", sampling_seed: int = 0, precise: bool = False):
         super().__init__(cfg, batch_size, device, every_n, num_inputs_L1, base_learning_rate,
                          clip_gradient_norm, regularization_penalty, shard_optimizer, learning_rate_decay,
                          learning_rate_decay_examples, sampling, sampling_seed)
-        self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain)
+        self.student = HLstmParams("model_student", cfg, device, student_seed, lstm_gain, precise)
         self.s_eng = HLstmEngine(self.student, batch_size, self.student_frames, num_inputs_L1, training=True)
         self.rows = torch.zeros(1, batch_size, dtype=torch.float32, device=self.device)
         self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)

@@ -134,7 +134,8 @@ def test_argument_errors_are_reported_before_any_launch():
     def call(**kw):
         a = dict(args, **kw)
         return lib.evc_lstm_seq_fwd_steps(a["x"], a["stride"], a["Kx"], a["W"], a["bias"], a["rows"], a["H"], a["T"],
-                                          a["t0"], a["t1"], None, None, None, None, None, 0, None)
+                                          a["t0"], a["t1"], None, None, None, None, None, 0, None, None, None, None,
+                                          None)
     assert call(rows=0) == -1 and b"empty" in lib.evc_last_error()
     for t0, t1 in ((-1, 2), (3, 2), (0, 5), (2, 2)):
         assert call(t0=t0, t1=t1) == -1 and b"step range" in lib.evc_last_error()
@@ -142,9 +143,17 @@ def test_argument_errors_are_reported_before_any_launch():
     with pytest.raises(_lib.EvcError, match="step range"):
         _lib.check(call(t0=3, t1=1), "evc_lstm_seq_fwd_steps")
     # evc_frames_pack: frames must split evenly into chunks (tf.split), features a multiple of 4
-    assert lib.evc_frames_pack(None, 2, 300, 128, None, 0, 30, 7, 1, None, None, None) == -1
+    assert lib.evc_frames_pack(None, 2, 300, 128, None, 0, 30, 7, 1, None, None, None, None) == -1
     assert b"split evenly" in lib.evc_last_error()
-    assert lib.evc_frames_pack(None, 2, 300, 126, None, 0, 30, 5, 1, None, None, None) == -1
+    assert lib.evc_frames_pack(None, 2, 300, 126, None, 0, 30, 5, 1, None, None, None, None) == -1
+    # split-bf16 mode: the residual planes come as a set
+    one = ctypes.c_void_p(16)
+    assert lib.evc_gemm_bf16x2(one, None, 0, 64, one, one, 0, 64, 128, 128, 64, one, 0, 128, None, 1, 0, None) == -1
+    assert b"lo planes" in lib.evc_last_error()
+    assert lib.evc_lstm_seq_fwd_steps(None, 0, 128, None, None, 128, 128, 4, 0, 4, None, None, None, None, None, 0,
+                                      one, None, None, None, None) == -1 and b"split-bf16" in lib.evc_last_error()
+    assert lib.evc_lstm_seq_fwd_resident(None, 0, 128, None, None, 100000, 1024, 4, None, None, None, None, None, 0,
+                                         None) == -3 and b"not eligible" in lib.evc_last_error()
     # evc_topk: k must be positive and <= num_classes (eval_util.py:103-104)
     assert lib.evc_topk(None, 4, 100, 0, None, None, None, None, None) == -1
     assert lib.evc_topk(None, 4, 100, 101, None, None, None, None, None) == -1

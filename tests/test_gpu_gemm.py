@@ -177,3 +177,91 @@ def test_lstm_seq_fwd_resident_matches_per_step_path(rows, Kx, H, T, train):
     # a second run over the same buffers (flags are reset by the call): deterministic, bit-identical
     h3, c3, _ = run(ops.lstm_seq_fwd_resident, ws_rec)
     assert torch.equal(h1, h3) and torch.equal(c1, c3)
+
+
+def _split(t):
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_split_bf16_precise_mode(a_mn, b_mn):
+    """evc_gemm_bf16x2: A_hi*B_hi + A_hi*B_lo + A_lo*B_hi in one f32 accumulator; ~2^-16 relative operand error
+    instead of 2^-9 (measured against the f64 product of the f32 operands), all operand majors, split-K and M/N
+    tails."""
+    from efficientvideoclassification_youtube8m_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 712, 520, 2048          # M, N tails; pitches stay multiples of 8 elements (TMA)
+    A = torch.randn(M, K, device="cuda")
+    Bm = torch.randn(K, N, device="cuda")
+    ref = A.double() @ Bm.double()
+    scale = ref.abs().max().item()
+    ah, al = _split(A.t().contiguous() if a_mn else A)
+    bh, bl = _split(Bm if b_mn else Bm.t().contiguous())
+    out = torch.zeros(M, N, device="cuda")
+    ops.gemm(ah, bh, M, N, K, out, a_mn=a_mn, b_mn=b_mn, A_lo=al, B_lo=bl)
+    err2 = (out.double() - ref).abs().max().item()
+    plain = torch.zeros(M, N, device="cuda")
+    ops.gemm(ah, bh, M, N, K, plain, a_mn=a_mn, b_mn=b_mn)
+    err1 = (plain.double() - ref).abs().max().item()
+    assert err2 < 2e-5 * scale, (err2, scale)            # measured ~3e-6: f32 accumulation + the dropped lo*lo term
+    assert err1 > 50 * err2                               # the plain bf16 product is two orders of magnitude coarser
+    acc = torch.ones(M, N, device="cuda")
+    ops.gemm(ah, bh, M, N, K, acc, a_mn=a_mn, b_mn=b_mn, split_k=4, accumulate=True, A_lo=al, B_lo=bl)
+    torch.cuda.synchronize()
+    assert (acc.double() - 1 - ref).abs().max().item() < 2e-5 * scale
+    with pytest.raises(Exception, match="lo plane"):
+        ops.gemm(ah, bh, M, N, K, out, a_mn=a_mn, b_mn=b_mn, A_lo=al)
+
+
+def test_lstm_seq_precise_mode_fwd_bwd():
+    """One BasicLSTM layer in split-bf16 mode (lo planes of x, W, h, gates, dz) against the f64 reference: state and
+    gradient errors two orders of magnitude below the plain-bf16 tolerances, at a row count above the small-row limit
+    (the precise mode routes every row count through the slab path)."""
+    from efficientvideoclassification_youtube8m_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    rows, Kx, H, T = 1300, 256, 128, 4
+    ws = torch.empty(ops.lstm_workspace_bytes(rows, H, Kx, True), dtype=torch.uint8, device=dev)
+    xf = torch.randn(T, rows, Kx, device=dev) * 0.5
+    Wf = torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)
+    b = torch.randn(4 * H, device=dev) * 0.1
+    x, x_lo = _split(xf)
+    W, W_lo = _split(Wf)
+    seq_len = torch.randint(0, T + 1, (rows,), device=dev, dtype=torch.int32)
+    seq_len[:4] = torch.tensor([0, 1, T, T - 1], dtype=torch.int32)
+    h_all, h_lo = (torch.zeros(T + 1, rows, H, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    c_all = torch.zeros(T + 1, rows, H, device=dev)
+    gates, gates_lo = (torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, ws, x_lo=x_lo, W_lo=W_lo,
+                     h_lo_all=h_lo, gates_lo_all=gates_lo)
+    xd = xf.double().requires_grad_(True)
+    Wd = Wf.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    c_ref, h_ref, hs_ref = _lstm_ref(xd, Wd, bd, seq_len, T, H)
+    assert (c_all[T].double() - c_ref).abs().max().item() < 2e-4
+    assert ((h_all[T].float() + h_lo[T].float()).double() - h_ref).abs().max().item() < 2e-4
+    dc_f, dh_f = torch.randn(rows, H, device=dev), torch.randn(rows, H, device=dev)
+    loss = (dc_f.double() * c_ref).sum() + (dh_f.double() * h_ref).sum()
+    gx, gW, gb = torch.autograd.grad(loss, [xd, Wd, bd])
+    dz, dz_lo = (torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    dh_pass, dc = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev)
+    db = torch.zeros(4 * H, device=dev)
+    ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, None, dh_f, H, dc_f, H, dh_pass, dc, dz, ws, dbias=db,
+                     W_lo=W_lo, gates_lo_all=gates_lo, dz_lo_all=dz_lo)
+    R = T * rows
+    dW = torch.zeros(Kx + H, 4 * H, device=dev)
+    ops.gemm(x.view(R, Kx), dz.view(R, 4 * H), Kx, 4 * H, R, dW[:Kx], a_mn=True, b_mn=True, ldc=4 * H,
+             A_lo=x_lo.view(R, Kx), B_lo=dz_lo.view(R, 4 * H))
+    ops.gemm(h_all.view(-1, H), dz.view(R, 4 * H), H, 4 * H, R, dW[Kx:], a_mn=True, b_mn=True, ldc=4 * H,
+             A_lo=h_lo.view(-1, H), B_lo=dz_lo.view(R, 4 * H))
+    dX = torch.zeros(R, Kx, device=dev)
+    ops.gemm(dz.view(R, 4 * H), W, R, Kx, 4 * H, dX, A_lo=dz_lo.view(R, 4 * H), B_lo=W_lo)
+    torch.cuda.synchronize()
+
+    def rel(a, bref):
+        return ((a.double() - bref).norm() / (bref.norm() + 1e-30)).item()
+    assert rel(dW, gW) < 3e-4, rel(dW, gW)
+    assert rel(dX.view(T, rows, Kx), gx) < 3e-4, rel(dX.view(T, rows, Kx), gx)
+    assert rel(db, gb) < 3e-4, rel(db, gb)
