@@ -9,10 +9,13 @@ GPU, 300 frames x 1152-d, every_n=10, 2x1024 LSTM cells, 2 mixtures, 4716 classe
 inputs.  One JSON line is printed by rank 0 (see the driver contract in the task statement).
 
   value    videos/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e      videos/s through the public step API with the f32 batch copied from pinned host memory
-           every step (double buffered on a copy stream) and the losses + top-20 read back
-  e2e_uint8_input / e2e_tfrecord_input   the same with the quantised uint8 batch a tfrecord holds, and with
-           the batch decoded from a TFRecord shard on disk by the native reader inside the timed loop
+  e2e      videos/s through the public step API with the quantised uint8 batch (what the tfrecords hold) copied
+           from pinned host memory every step (double buffered on a copy stream), Dequantize fused into the pack
+           kernel, and the losses + top-20 read back
+  e2e_f32_input / e2e_tfrecord_input   the same with the dequantised float32 batch (4x the bytes), and with the
+           batch decoded from a TFRecord shard on disk by the native reader inside the timed loop (every rank its own)
+  configs  BASELINE configs #4 (fine-tune, 2048 cells x 4 mixtures), #5 (every_n sweep, random vs uniform) and the
+           split-bf16 precise mode, a few steps each (one GPU)
   roofline dominant kernel = fused LSTM forward step GEMM of the teacher's lower level, timed alone
   cpu_baseline  the float32 PyTorch-CPU restatement (oracle/, "port": TensorFlow 1.x is not
            installable here) on a bounded sample, on the host's cores
@@ -140,15 +143,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def _tfrecord_e2e(tr, B, dev, steps, ops):
-    """videos/s of shard files -> reader -> GPU step -> host results (one shard of B synthetic videos, read
-    `steps + warm-up` times; the page cache holds it, as it would hold a training set's hot shards)."""
+def _tfrecord_e2e(tr, B, dev, steps, ops, rank=0):
+    """videos/s of shard files -> reader -> GPU step -> host results (one shard of B synthetic videos per rank,
+    read `steps + warm-up` times; the page cache holds it, as it would hold a training set's hot shards)."""
     import tempfile
     import torch
     from efficientvideoclassification_youtube8m_b200 import readers as R
-    rng = np.random.default_rng(77)
+    rng = np.random.default_rng(77 + rank)
     tmp = tempfile.mkdtemp(prefix="evc_bench_")
-    path = os.path.join(tmp, "train0.tfrecord")
+    path = os.path.join(tmp, "train%d.tfrecord" % rank)
     recs = []
     for i in range(B):
         recs.append(R.make_sequence_example(
@@ -158,7 +161,8 @@ def _tfrecord_e2e(tr, B, dev, steps, ops):
     R.write_tfrecord(path, recs, with_crc=True)
     warm = 2
     rd = R.YT8MFrameFeatureReader(feature_names=["rgb", "audio"], feature_sizes=[1024, 128])
-    it = rd.batches([path] * (steps + warm), B, native=True, verify_crc=True, prefetch=2)
+    threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
+    it = rd.batches([path] * (steps + warm), B, native=True, verify_crc=True, prefetch=2, num_threads=threads)
     xq = torch.empty(B, 300, 1152, dtype=torch.uint8, device=dev)
     nfd = torch.empty(B, dtype=torch.int32, device=dev)
     lab = torch.empty(B, 4716, dtype=torch.bool, device=dev)
@@ -188,9 +192,24 @@ def _tfrecord_e2e(tr, B, dev, steps, ops):
         os.rmdir(tmp)
     except OSError:
         pass
-    return {"value": B / (ms * 1e-3), "unit": "videos/s", "ms_per_step": ms, "wall_ms_per_step": wall_ms,
-            "shard_bytes_per_step": B * 300 * 1152, "reader": "libevc_reader, CRC32C verified, prefetch 2",
-            "reader_threads": os.cpu_count()}
+    return {"ms_per_step": ms, "wall_ms_per_step": wall_ms, "shard_bytes_per_step": B * 300 * 1152,
+            "reader": "libevc_reader, CRC32C verified, prefetch 2", "reader_threads": threads}
+
+
+def _profile_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    --set full summary of this round (profiles/r02_ncu_fwd_gemm.json written by scripts/ncu_summary.py); the
+    bench itself never runs under a profiler."""
+    for name in ("r02_ncu_fwd_gemm.json", "r01_ncu_fwd_gemm.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                with open(p) as f:
+                    d = json.load(f)
+                return float(d["dram_bytes_per_launch"]), "profiles/" + name
+            except Exception:   # noqa: BLE001
+                pass
+    return 100.8e6, "profiles/r01_ncu_kernels_summary.txt (64.5 MB read + 36.3 MB written per launch)"
 
 
 def run_ours(args):
@@ -212,23 +231,35 @@ def run_ours(args):
     B = args.batch
     finetune = args.workload == "finetune_cfg4"
     cfg = ModelConfig(lstm_cells=2048, num_mixtures=4) if finetune else ModelConfig()
-    # Reference hyper-parameters except the learning rate: with the default 1e-3, Adam saturates the
-    # MoE on a *repeated* synthetic batch within ~5 steps (p -> 0, KL -> inf; the reference's
-    # check_numerics would abort the same way).  The optimizer does identical work at any lr.
+    # Reference hyper-parameters (run_train.sh / train.py defaults: Adam, clip 1.0, regularization_penalty 2) except
+    # the learning rate.  On THESE synthetic inputs (uniform random features, random labels) the reference graph
+    # itself diverges at its default lr 1e-3: the float32 CPU oracle reaches |state| = 18 and a NaN L_PRED at step
+    # 4, rotating batches or not (tests/divergence_full_size.py, recorded in
+    # profiles/r02_oracle_divergence_lr1e-3.json; check_numerics would abort the reference there), while it stays
+    # finite at 1e-5 (profiles/r02_oracle_finite_lr1e-5.json).  The optimizer does identical work at any lr; the
+    # step sees NB different batches in rotation, like a training run.
     if finetune:   # BASELINE configs[3]: student fine-tune, lstm_cells 2048, 4 mixtures, clip 1.0
-        tr = StudentFinetuneTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr)
+        tr = StudentFinetuneTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr, precise=args.precise)
     else:
-        tr = TeacherStudentTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr)
+        tr = TeacherStudentTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr, precise=args.precise)
 
-    # synthetic batch: two host-pinned copies (double buffering) + a resident one
-    x, nf, lab = O.synthetic_batch(B, seed=1234 + rank, full_length=True)
-    host_x = [torch.from_numpy(x).pin_memory(), torch.from_numpy(x.copy()).pin_memory()]
-    host_nf = torch.from_numpy(nf).pin_memory()
-    host_lab = torch.from_numpy(lab).view(torch.uint8).pin_memory()
-    dx = [torch.empty_like(host_x[0], device=dev) for _ in range(2)]
-    dnf = torch.empty_like(host_nf, device=dev)
-    dlab = torch.empty_like(host_lab, device=dev)
-    dx[0].copy_(host_x[0]); dnf.copy_(host_nf); dlab.copy_(host_lab)
+    # synthetic batches: NB quantised (uint8, what a tfrecord holds) host-pinned batches; the device-resident
+    # timing uses their dequantised float32 form (the tensor the reference's reader hands to the graph)
+    NB = args.batches
+    hq, hlab, dxf = [], [], []
+    for i in range(NB):
+        rng = np.random.default_rng(1234 + 1000 * rank + i)
+        q = rng.integers(0, 256, size=(B, 300, 1152), dtype=np.uint8)
+        _, _, lab = O.synthetic_batch(B, seed=4321 + 1000 * rank + i, num_features=4, full_length=True)
+        hq.append(torch.from_numpy(q).pin_memory())
+        hlab.append(torch.from_numpy(lab).view(torch.uint8).pin_memory())
+    host_nf = torch.full((B,), 300, dtype=torch.int32).pin_memory()
+    dnf = host_nf.to(dev)
+    dlab = [h.to(dev) for h in hlab]
+    for i in range(NB):                    # Dequantize on the device (bit-identical to utils.Dequantize, tests)
+        xf = torch.empty(B, 300, 1152, dtype=torch.float32, device=dev)
+        ops.frames_pack_u8(hq[i].to(dev), dnf, None, 300, 1, False, out_f32=xf)
+        dxf.append(xf)
     torch.cuda.synchronize()
 
     def barrier():
@@ -254,75 +285,104 @@ def run_ours(args):
         return ms / steps
 
     # ---------------- device-resident timing (value)
-    # the 354 MB input batch plus >3 GB of activations written and re-read per step exceed the
-    # 126 MB L2, so consecutive steps do not find their inputs cached
+    # every step reads a different 354 MB batch and writes + re-reads >3 GB of activations: nothing a step needs
+    # is left in the 126 MB L2 by the previous one
     sampler = ClockSampler(local_rank)
+    state = {"i": 0}
+
+    def resident_step():
+        i = state["i"] % NB
+        state["i"] += 1
+        tr.step(dxf[i], dnf, dlab[i])
+
     n0 = _lib.launch_count()
-    tr.step(dx[0], dnf, dlab)
+    resident_step()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - n0
     sampler.start()
-    ms_step = timed(lambda: tr.step(dx[0], dnf, dlab), args.steps, args.warmup)
-    losses = tr.fetch()
+    ms_step = timed(resident_step, args.steps, args.warmup)
+    try:
+        losses = tr.fetch()
+    except FloatingPointError as e:      # the reference's check_numerics would stop training here
+        losses = {"error": str(e)}
 
-    # ---------------- end to end through the public step API, host buffers (e2e)
+    # ---------------- end to end through the public step API, HOST buffers (e2e): the quantised uint8 batch a
+    # tfrecord holds travels from pinned host memory every step (double buffered on a copy stream), Dequantize
+    # runs inside the pack kernel, the losses and the student's top-20 come back
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
     out_host = torch.empty(tr.losses.numel(), dtype=torch.float32).pin_memory()
     topk_host = torch.empty(B, 20, dtype=torch.int32).pin_memory()
-    state = {"i": 0}
+    pred_eng = tr.s_eng
 
-    def prefetch(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[slot])
-            dx[slot].copy_(host_x[slot], non_blocking=True)
-            dnf.copy_(host_nf, non_blocking=True)
-            dlab.copy_(host_lab, non_blocking=True)
-            ready[slot].record(copy_stream)
+    def make_e2e(host_x, dev_x):
+        st = {"i": 0}
+        dl = [torch.empty_like(hlab[0], device=dev) for _ in range(2)]
+        dn = torch.empty_like(host_nf, device=dev)
 
-    freed[0].record(main); freed[1].record(main)
-    prefetch(0)
+        def prefetch(slot, i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[slot])
+                dev_x[slot].copy_(host_x[i % NB], non_blocking=True)
+                dn.copy_(host_nf, non_blocking=True)
+                dl[slot].copy_(hlab[i % NB], non_blocking=True)
+                ready[slot].record(copy_stream)
 
-    def e2e_step():
-        slot = state["i"] & 1
-        prefetch(slot ^ 1)                       # next batch travels while this one computes
-        main.wait_event(ready[slot])
-        tr.step(dx[slot], dnf, dlab)
-        idx, val, _ = ops.topk(tr.s_eng.pred, 20)
-        freed[slot].record(main)
-        out_host.copy_(tr.losses, non_blocking=True)
-        topk_host.copy_(idx, non_blocking=True)
-        main.synchronize()                       # the step's result is on the host
-        state["i"] += 1
+        def step():
+            slot = st["i"] & 1
+            prefetch(slot ^ 1, st["i"] + 1)          # next batch travels while this one computes
+            main.wait_event(ready[slot])
+            tr.step(dev_x[slot], dn, dl[slot])
+            idx, val, _ = ops.topk(pred_eng.pred, 20)
+            freed[slot].record(main)
+            out_host.copy_(tr.losses, non_blocking=True)
+            topk_host.copy_(idx, non_blocking=True)
+            main.synchronize()                       # the step's result is on the host
+            st["i"] += 1
 
-    ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
-    clocks = sampler.stop()          # sampled over both timed regions (device-resident and e2e)
+        main.synchronize(); copy_stream.synchronize()
+        freed[0].record(main); freed[1].record(main)
+        prefetch(0, 0)
+        return step
 
-    # same loop fed with the quantised uint8 features a tfrecord holds (readers.YT8MFrameFeatureReader):
-    # Dequantize + zero padding run inside the pack kernel, 4x fewer bytes cross PCIe
-    rngq = np.random.default_rng(1234 + rank)
-    hq = torch.from_numpy(rngq.integers(0, 256, size=x.shape, dtype=np.uint8)).pin_memory()
-    dq = [torch.empty_like(hq, device=dev) for _ in range(2)]
-    host_x[0], host_x[1], dx[0], dx[1] = hq, hq, dq[0], dq[1]
-    main.synchronize(); copy_stream.synchronize()
-    freed[0].record(main); freed[1].record(main)
-    state["i"] = 0
-    prefetch(0)
-    ms_e2e_u8 = timed(e2e_step, max(3, args.steps // 2), 2)
-    h2d = host_x[0].numel() * 4 + host_nf.numel() * 4 + host_lab.numel()
+    e2e_steps = max(3, args.steps // 2)
+    dq = [torch.empty_like(hq[0], device=dev) for _ in range(2)]
+    ms_e2e = timed(make_e2e(hq, dq), e2e_steps, 2)
+    h2d = hq[0].numel() + host_nf.numel() * 4 + hlab[0].numel()
     d2h = out_host.numel() * 4 + topk_host.numel() * 4
+    del dq
+    # the same loop fed with the dequantised float32 batch (4x the bytes over PCIe): what the reference's reader
+    # queue hands to the graph
+    e2e_f32 = None
+    if not args.skip_f32_e2e:
+        hf = [x.cpu().pin_memory() for x in dxf[:2]]
+        df = [torch.empty_like(dxf[0]) for _ in range(2)]
+        hx = [hf[i % 2] for i in range(NB)]
+        ms_f32 = timed(make_e2e(hx, df), e2e_steps, 2)
+        e2e_f32 = {"value": world * B / (ms_f32 * 1e-3), "unit": "videos/s", "ms_per_step": ms_f32,
+                   "h2d_bytes_per_step": hf[0].numel() * 4 + host_nf.numel() * 4 + hlab[0].numel()}
+        del hf, df, hx
+    clocks = sampler.stop()          # sampled over the device-resident and e2e timed regions
 
     # ---------------- the whole input path: TFRecord shards on disk -> native reader (libevc_reader, uint8
-    # batches decoded into pinned memory on a background thread) -> H2D -> step -> results on the host.
-    # Extra information only: a failure here must not cost the bench line.
+    # batches decoded into pinned memory on a background thread) -> H2D -> step -> results on the host; every rank
+    # reads its own shard.  Extra information only: a failure here must not cost the bench line.
     e2e_tfrecord = None
-    if world == 1 and not finetune and not args.skip_tfrecord:
+    if not finetune and not args.skip_tfrecord:
         try:
-            e2e_tfrecord = _tfrecord_e2e(tr, B, dev, max(3, args.steps // 2), ops)
+            r = _tfrecord_e2e(tr, B, dev, e2e_steps, ops, rank)
+            ms_t = r["ms_per_step"]
+            if world > 1:
+                t = torch.tensor([ms_t], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_t = t.item()
+            e2e_tfrecord = dict(r, value=world * B / (ms_t * 1e-3), unit="videos/s", ms_per_step=ms_t)
         except Exception as e:   # noqa: BLE001
             e2e_tfrecord = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise
 
     # ---------------- dominant kernel alone: RNN_L1 cell-0 forward steps of the teacher (15 launches; the
     # student's 6 for the fine-tune workload)
@@ -338,23 +398,23 @@ def run_ours(args):
     flops_seq = 2.0 * R1 * 4 * H * (D * ell + H * (ell - 1))
     peaks, peak_kind = _peaks()
     achieved = flops_seq / (ms_seq * 1e-3) / 1e12
+    traffic, traffic_src = _profile_traffic()
     roof = {"bound": "tensor", "kernel": "gemm_kernel<A=K,B=MN,BN=256,EPI_LSTM_FWD> (%s RNN_L1 cell 0, %d rows)"
             % ("student" if finetune else "teacher", R1),
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
-            # capture summarised in profiles/r01_ncu_kernels_summary.txt (64.5 MB + 36.3 MB); the algorithmic
-            # bytes are 61 MB read (x_t, h, W, c) + 73.5 MB written (c, h, gates), the L2 absorbs part
-            "traffic": None if finetune else 100.8e6, "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst bf16",
-            "launches_timed": ell, "avg_launch_ms": ms_seq / ell}
+            # measured by ncu --set full in a separate run (never in the bench): algorithmic bytes are 61 MB read
+            # (x_t, h, W, c) + 73.5 MB written (c, h, gates) per launch, the L2 absorbs part of it
+            "traffic": None if finetune else traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
+            "peak_kind": peak_kind + " burst bf16", "launches_timed": ell, "avg_launch_ms": ms_seq / ell}
 
-    # ---------------- student inference (BASELINE config #2), device resident
-    infer = None
+    # ---------------- BASELINE configs #2, #4, #5 (one GPU, device resident, a few steps each)
+    infer, configs = None, None
     if world == 1 and not args.skip_infer and not finetune:
         Bi = 1024
         xi, nfi, _ = O.synthetic_batch(Bi, seed=99, full_length=True)
-        ev = StudentEvaluator(tr.student, Bi)
         dxi, dnfi = torch.from_numpy(xi).to(dev), torch.from_numpy(nfi).to(dev)
+        ev = StudentEvaluator(tr.student, Bi)
         ms_inf = timed(lambda: ev.step(dxi, dnfi), 10, 3)
         infer = {"student_infer_videos_per_s": Bi / (ms_inf * 1e-3), "batch": Bi, "ms_per_step": ms_inf}
         del ev
@@ -363,7 +423,40 @@ def run_ours(args):
         ms_t = timed(lambda: evt.step(dxi, dnfi), 5, 2)
         infer.update({"teacher_infer_videos_per_s": Bi / (ms_t * 1e-3), "teacher_ms_per_step": ms_t,
                       "student_speedup_over_teacher": ms_t / ms_inf})
-        del evt, dxi
+        del evt
+        if not args.skip_configs:
+            configs = {}
+            # #5: frame-budget sweep and random vs uniform sampling (student fine-tune step B=256, student inference
+            # B=1024; the student's own weights, cfg #1 dimensions)
+            sweep = {}
+            for every_n, sampling in ((5, "uniform"), (10, "uniform"), (20, "uniform"), (30, "uniform"),
+                                      (10, "random_frames"), (10, "random_sequence")):
+                ft = StudentFinetuneTrainer(ModelConfig(), batch_size=B, device=dev, every_n=every_n,
+                                            base_learning_rate=args.lr, sampling=sampling)
+                ms_ft = timed(lambda: ft.step(dxf[0], dnf, dlab[0]), 5, 3)
+                evs = StudentEvaluator(ft.student, Bi, every_n=every_n, sampling=sampling)
+                ms_ev = timed(lambda: evs.step(dxi, dnfi), 5, 3)
+                sweep[f"every_n={every_n},{sampling}"] = {
+                    "student_frames": ft.student_frames, "train_videos_per_s": B / (ms_ft * 1e-3),
+                    "train_ms_per_step": ms_ft, "infer_videos_per_s": Bi / (ms_ev * 1e-3), "infer_ms_per_step": ms_ev}
+                del ft, evs
+            configs["cfg5_frame_budget_and_sampling"] = sweep
+            # #4: student fine-tune with 2048 cells, 4 mixtures, clip 1.0
+            ft4 = StudentFinetuneTrainer(ModelConfig(lstm_cells=2048, num_mixtures=4), batch_size=B, device=dev,
+                                         base_learning_rate=args.lr)
+            ms4 = timed(lambda: ft4.step(dxf[0], dnf, dlab[0]), 5, 3)
+            configs["cfg4_student_finetune_2048x4"] = {
+                "train_videos_per_s": B / (ms4 * 1e-3), "ms_per_step": ms4,
+                "model_tflops": B / (ms4 * 1e-3) * GF_PER_VIDEO_FINETUNE_CFG4 / 1e3}
+            del ft4
+            # the joint step in split-bf16 "precise" mode (3 tensor-core products per contraction)
+            if not args.precise:
+                trp = TeacherStudentTrainer(ModelConfig(), batch_size=B, device=dev, base_learning_rate=args.lr,
+                                            precise=True)
+                msp = timed(lambda: trp.step(dxf[0], dnf, dlab[0]), 3, 2)
+                configs["cfg1_precise_split_bf16"] = {"train_videos_per_s": B / (msp * 1e-3), "ms_per_step": msp}
+                del trp
+        del dxi
 
     if rank == 0:
         vps = world * B / (ms_step * 1e-3)
@@ -373,7 +466,7 @@ def run_ours(args):
             "metric": "H-LSTM student fine-tune train videos/s" if finetune else
                       "H-LSTM teacher-student train videos/s", "value": vps, "unit": "videos/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2" if args.precise else "bf16", "data": "synthetic",
             "config": {"workload": "student fine-tune step (run_finetune.sh with lstm_cells 2048, 4 mixtures; "
                                    "BASELINE configs[3])" if finetune else
                                    "teacher-student joint train step (run_train.sh defaults; BASELINE configs[0]/[2])",
@@ -381,20 +474,22 @@ def run_ours(args):
                        "every_n": 10, "lstm_cells": cfg.lstm_cells, "lstm_layers": 2,
                        "moe_num_mixtures": cfg.num_mixtures,
                        "classes": 4716, "parallelism": f"dp{world}", "base_learning_rate": args.lr,
-                       "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2"},
+                       "rotating_batches": NB,
+                       "l2_policy": "a different 354 MB batch every step + >3 GB of activations per step exceed the "
+                                    "126 MB L2"},
             "model_tflops": vps * gf / 1e3,
             "frac_of_sustained_bf16_peak": vps * gf / 1e3 / world / peaks["bf16_tflops_sustained"],
             "e2e": {"value": e2e_vps, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e},
-            "e2e_uint8_input": {"value": world * B / (ms_e2e_u8 * 1e-3), "unit": "videos/s",
-                                "h2d_bytes_per_step": hq.numel() + host_nf.numel() * 4 + host_lab.numel(),
-                                "ms_per_step": ms_e2e_u8},
+                    "ms_per_step": ms_e2e, "input": "uint8 features as stored in the tfrecords, pinned host memory"},
+            "e2e_f32_input": e2e_f32,
             "e2e_tfrecord_input": e2e_tfrecord,
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roof, "losses": losses,
         }
         if infer:
             line["student_infer"] = infer
+        if configs:
+            line["configs"] = configs
         if world == 1 and not args.skip_cpu and not finetune:
             v, sec, cores = cpu_baseline(32, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port",
@@ -412,7 +507,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--lr", type=float, default=1e-5,
+                    help="base_learning_rate (train.py:75 default 1e-3 diverges on random synthetic inputs, also in "
+                         "the CPU oracle: profiles/r02_oracle_divergence_lr1e-3.json)")
+    ap.add_argument("--batches", type=int, default=8, help="distinct synthetic batches in rotation")
+    ap.add_argument("--precise", action="store_true", help="split-bf16 mode (3 products per contraction)")
+    ap.add_argument("--skip-f32-e2e", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true")
     ap.add_argument("--workload", default="ts_train", choices=["ts_train", "finetune_cfg4"])
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-infer", action="store_true")
