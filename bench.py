@@ -233,10 +233,10 @@ def run_ours(args):
     cfg = ModelConfig(lstm_cells=2048, num_mixtures=4) if finetune else ModelConfig()
     # Reference hyper-parameters (run_train.sh / train.py defaults: Adam, clip 1.0, regularization_penalty 2) except
     # the learning rate.  On THESE synthetic inputs (uniform random features, random labels) the reference graph
-    # itself diverges at its default lr 1e-3: the float32 CPU oracle reaches |state| = 18 and a NaN L_PRED at step
-    # 4, rotating batches or not (tests/divergence_full_size.py, recorded in
-    # profiles/r02_oracle_divergence_lr1e-3.json; check_numerics would abort the reference there), while it stays
-    # finite at 1e-5 (profiles/r02_oracle_finite_lr1e-5.json).  The optimizer does identical work at any lr; the
+    # itself diverges at its default lr 1e-3: the float32 CPU restatement reaches |state| = 18 and a NaN L_PRED at
+    # step 4, rotating batches or not (tests/divergence_full_size.py, recorded in
+    # profiles/r02_cpu_reference_divergence_lr1e-3.json; check_numerics would abort the reference there), while it
+    # stays finite at 1e-5 (profiles/r02_cpu_reference_finite_lr1e-5.json).  The optimizer does identical work at any lr; the
     # step sees NB different batches in rotation, like a training run.
     if finetune:   # BASELINE configs[3]: student fine-tune, lstm_cells 2048, 4 mixtures, clip 1.0
         tr = StudentFinetuneTrainer(cfg, batch_size=B, device=dev, base_learning_rate=args.lr, precise=args.precise)
@@ -509,7 +509,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--lr", type=float, default=1e-5,
                     help="base_learning_rate (train.py:75 default 1e-3 diverges on random synthetic inputs, also in "
-                         "the CPU oracle: profiles/r02_oracle_divergence_lr1e-3.json)")
+                         "the CPU restatement: profiles/r02_cpu_reference_divergence_lr1e-3.json)")
     ap.add_argument("--batches", type=int, default=8, help="distinct synthetic batches in rotation")
     ap.add_argument("--precise", action="store_true", help="split-bf16 mode (3 products per contraction)")
     ap.add_argument("--skip-f32-e2e", action="store_true")

@@ -218,7 +218,7 @@ class HLstmParams:
 
     def apply_gradients_sharded(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
                                 rank: int, world: int, group=None, beta1: float = 0.9, beta2: float = 0.999,
-                                eps: float = 1e-8):
+                                eps: float = 1e-8, gather: bool = True):
         """Same update as apply_gradients for the rows this rank owns.  Expects the matrix gradients
         reduce-scattered (owned rows = average over ranks) and the bias gradients all-reduced.  Returns the
         async all-gather handles of the bf16 operand copies (wait before the next forward)."""
@@ -252,6 +252,8 @@ class HLstmParams:
                               self.normsq[i:i + 1], float(clip_gradient_norm), wd if n in reg else 0.0, self.lr_t,
                               beta1, beta2, eps, self.shadow[n][r0:r1], cols, ld,
                               self.shadow_lo[n][r0:r1] if self.precise else None)
+                if not gather:          # attribution experiments only (EVC_DP_ABLATE=2)
+                    continue
                 handles.append(dist.all_gather_into_tensor(self.shadow[n], self.shadow[n][r0:r1], group=group,
                                                            async_op=True))
                 if self.precise:

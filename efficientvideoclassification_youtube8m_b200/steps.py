@@ -76,8 +76,11 @@ class _Base:
             self.frame_idx_rand = torch.empty(batch_size, K, dtype=torch.int32, device=self.device)
         self.global_step = 0
         self._pending = []
-        self._gathers = []
+        self._gathers = {}          # id(params) -> outstanding all-gathers of that model's bf16 operand rows
         self._opt_streams = {}
+        # attribution experiments only (profiles/r02_dp_ablation.md): 1 = no gradient collectives, 2 = no operand
+        # all-gathers -- the step then computes garbage across ranks but keeps its kernel schedule
+        self._dp_ablate = int(os.environ.get("EVC_DP_ABLATE", "0"))
         # optimizer sharding over the data-parallel ranks (on by default when there is more than one)
         self.shard_optimizer = shard_optimizer if shard_optimizer is not None else (self._world() > 1)
 
@@ -139,7 +142,7 @@ class _Base:
         mode, per-matrix reduce-scatter (owner keeps the average of its row block) + bias all-reduce in the
         sharded mode.  Asynchronous on NCCL's stream."""
         n = self._world()
-        if n <= 1:
+        if n <= 1 or (self._dp_ablate & 1):
             return
         if not (self.shard_optimizer and dist.get_backend() == "nccl"):
             lo = min(params.offsets[x] for x in names)
@@ -161,7 +164,9 @@ class _Base:
         self._finish_allreduce(params)
         n = self._world()
         if n > 1 and self.shard_optimizer and dist.get_backend() == "nccl":
-            self._gathers += params.apply_gradients_sharded(self.lr, self.clip, self.penalty, dist.get_rank(), n)
+            self._gathers.setdefault(id(params), []).extend(
+                params.apply_gradients_sharded(self.lr, self.clip, self.penalty, dist.get_rank(), n,
+                                               gather=not (self._dp_ablate & 2)))
         else:
             params.apply_gradients(self.lr, self.clip, self.penalty)
 
@@ -193,10 +198,14 @@ class _Base:
         params.apply_gradients(self.lr, self.clip, self.penalty, first=0, last=8, advance=False)
         torch.cuda.current_stream().wait_stream(self._opt_stream(params)[0])
 
-    def _finish_gathers(self):
-        for w in self._gathers:
-            w.wait()
-        self._gathers = []
+    def _finish_gathers(self, params=None):
+        """Make the current stream wait for the outstanding operand all-gathers of one model (or of all).  They are
+        issued at the end of a step and only needed by the NEXT forward of that model, so the wait sits there: the
+        teacher's forward starts while the student's rows are still on the wire."""
+        keys = list(self._gathers) if params is None else [id(params)]
+        for k in keys:
+            for w in self._gathers.pop(k, []):
+                w.wait()
 
     def _finish_allreduce(self, params=None):
         """Wait for the outstanding collectives (of one parameter set, or all)."""
@@ -261,8 +270,10 @@ class TeacherStudentTrainer(_Base):
         side.wait_stream(main)                       # the batch (and last step's weights) are ready
         # (the teacher's launches are issued first: when the host starts a step on an idle device, its large
         # kernels should be in the queue before the student's small ones)
+        self._finish_gathers(self.teacher)
         t.forward(raw, None, True, num_frames, num_frames, mix=False)
         with torch.cuda.stream(side):
+            self._finish_gathers(self.student)
             idx = self._student_sample(num_frames, u)
             s.forward(raw, idx, True, self.nf_student, num_frames, mix=False)
         t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
@@ -305,8 +316,10 @@ class TeacherStudentTrainer(_Base):
         B = self.B
         t, s = self.t_eng, self.s_eng
         # teacher: create_model on the normalised 300 frames (train.py:256,281-288)
+        self._finish_gathers(self.teacher)
         t.forward(raw, None, True, num_frames, num_frames, mix=False)
         # student: every_n-th frame, float64 length rule (train.py:262-272,349-357) -- or a random sampler
+        self._finish_gathers(self.student)
         idx = self._student_sample(num_frames, u)
         s.forward(raw, idx, True, self.nf_student, num_frames, mix=False)
         # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term.
@@ -339,7 +352,6 @@ class TeacherStudentTrainer(_Base):
             torch.cuda.current_stream().wait_stream(self.student_stream)
         else:
             self._apply(self.student)
-        self._finish_gathers()
 
     def step(self, model_input_raw, num_frames, labels, u=None) -> None:
         """One iteration = both train ops (global_step += 2).  Asynchronous; read
@@ -357,6 +369,7 @@ class TeacherStudentTrainer(_Base):
     def fetch(self) -> Dict[str, float]:
         """Device->host read of the step's scalars (the reference fetches them in sess.run and
         checks the loss with check_numerics)."""
+        self._finish_gathers()      # (a host sync point: whoever reads the weights next sees complete operand copies)
         v = self.losses.tolist()
         wsq_t = self.teacher.wsq.tolist()
         wsq_s = self.student.wsq.tolist()
@@ -391,6 +404,7 @@ class StudentFinetuneTrainer(_Base):
     def step(self, model_input_raw, num_frames, labels, u=None) -> None:
         self._check(model_input_raw, num_frames, labels)
         B, s = self.B, self.s_eng
+        self._finish_gathers(self.student)
         idx = self._student_sample(num_frames, u)
         s.forward(model_input_raw, idx, True, self.nf_student, num_frames, mix=False)
         s.classifier_loss_fused(_as_u8(labels), None, 1.0 / B, 0.0, self.rows[0], None)
@@ -406,10 +420,10 @@ class StudentFinetuneTrainer(_Base):
             self._apply_lstm_late(self.student)
         else:
             self._apply(self.student)
-        self._finish_gathers()
         self.global_step += 1
 
     def fetch(self) -> Dict[str, float]:
+        self._finish_gathers()
         v = self.losses.tolist()
         wsq = self.student.wsq.tolist()
         reg = self.cfg.l2_penalty * 0.5 * (wsq[8] + wsq[9])
