@@ -227,6 +227,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # (the image's default prints a version banner on stdout)
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     finetune = args.workload == "finetune_cfg4"

@@ -160,7 +160,7 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
                       int K, void* C, int c_bf16, long long ldc, const float* bias, int split_k, int accumulate,
                       cudaStream_t stream, int force_bn = 0, long long split_stride = 0, int* splits_out = nullptr,
                       const void* A2 = nullptr, int K1 = 0, const void* A_lo = nullptr, const void* B_lo = nullptr,
-                      const void* A2_lo = nullptr) {
+                      const void* A2_lo = nullptr, bool stream_k = false) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "gemm: empty problem");
   // split-bf16 "precise" product: both residual planes or none (same shapes / pitches as the hi planes)
   const bool x2 = A_lo != nullptr || B_lo != nullptr;
@@ -168,7 +168,13 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
     return set_error(EVC_ERR_ARG, "gemm: split-bf16 mode needs the lo plane of every operand");
   if (split_k < 1) split_k = 1;
   if ((split_k > 1 || accumulate) && c_bf16) return set_error(EVC_ERR_ARG, "gemm: split-K/accumulate needs f32 C");
-  const int bn = force_bn ? force_bn : ((N > 128) ? 256 : 128);
+  int bn = force_bn ? force_bn : ((N > 128) ? 256 : 128);
+  // weight-streaming regime (few rows, wide N: the MoE logits GEMMs, 256 x 9432 x 4096): 128 x 256 tiles give fewer
+  // work items than SMs (74 of 148) and stream the weights at a fraction of the HBM rate; 128-wide tiles fill the chip
+  if (!force_bn && bn == 256 && split_k <= 1 &&
+      static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 256) < num_sms() &&
+      static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 128) > static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 256))
+    bn = 128;
   GemmArgs g = {};
   g.M = M; g.N = N;
   g.tiles_m = ceil_div(M, BM);
@@ -215,6 +221,19 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   if (x2) {
     rc = make_tmap_b(&tblo, B_lo, b_mn, ldb, N, K, bn, cs);
     if (rc) return rc;
+  }
+  if (stream_k) {
+    // stream-K over two slabs (see WorkIter): every cluster gets an equal share of the (tile, k-block) space
+    const long long ctiles = static_cast<long long>(ceil_div(g.tiles_m, cs)) * g.tiles_n;
+    const int clusters = num_sms() / cs;
+    // (not eligible -- fewer tiles than clusters, no slab output -- : the static split-K schedule as requested)
+    if (split_stride != 0 && ctiles >= clusters && g.kb_total >= 2) {
+      g.stream_k = 1;
+      g.split_k = 2;
+      g.kb_per_split = g.kb_total;
+      g.atomic_add = 0;
+      if (splits_out) *splits_out = 2;
+    }
   }
   const CUtensorMap* pa = x2 ? &talo : nullptr;
   const CUtensorMap* pa2 = x2 ? &ta2lo : nullptr;
@@ -297,7 +316,8 @@ extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx, int preci
   // forward small-row path: S x rows x 4H f32 ; backward: S x rows x H f32
   // (precise = split-bf16 mode: every forward step goes through the slab path, whatever the row count)
   int sf = (rows <= 1024 || precise) ? pick_split(ceil_div(rows, BM) * (4 * H / 256), (Kx + H) / BK) : 0;
-  const int sb = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
+  int sb = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
+  if (sb < 2) sb = 2;   // the stream-K schedule of the recurrent dgrad writes two slabs
   const long long f = static_cast<long long>(sf) * rows * 4 * H * 4;
   const long long b = static_cast<long long>(sb) * rows * H * 4;
   return (f > b ? f : b) + 256;
@@ -528,8 +548,15 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     float* part = static_cast<float*>(workspace);
     // (128x128 tiles without split-K -- twice the tiles, half the slab traffic -- measured 2 % slower per step)
     const int want = pick_split(ceil_div(rows, BM) * ceil_div(H, 256), 4 * H / BK);
-    if (static_cast<long long>(want) * RH * 4 > workspace_bytes)
+    if (static_cast<long long>(want < 2 ? 2 : want) * RH * 4 > workspace_bytes)
       return set_error(EVC_ERR_ARG, "lstm_seq_bwd: workspace too small (evc_lstm_workspace_bytes)");
+    // stream-K (two slabs, every cluster the same number of k blocks) when there are more tiles than clusters:
+    // the 160 tiles of the 5120-row dgrad otherwise quantise into 3 rounds for 2.16 rounds of work
+    static int use_sk = -1;
+    if (use_sk < 0) {
+      const char* e = getenv("EVC_STREAMK");
+      use_sk = e ? atoi(e) : 1;
+    }
     if (dbias != nullptr) {
       cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * 4 * H, stream);
       if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(dbias)");
@@ -539,7 +566,8 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
       int splits = 0;
       if (!last) {
         int rc = gemm_store(zb + (t + 1) * RH * 4, 0, 4LL * H, wh, 0, 4LL * H, rows, H, 4 * H, part, 0, H, nullptr,
-                            want, 0, stream, 256, RH, &splits, nullptr, 0, x2 ? zl + (t + 1) * RH * 4 : nullptr, whl);
+                            want, 0, stream, 256, RH, &splits, nullptr, 0, x2 ? zl + (t + 1) * RH * 4 : nullptr, whl,
+                            nullptr, use_sk != 0);
         if (rc) return rc;
       }
       int rc = launch_lstm_cell_bwd(part, splits, RH, gb + t * RH * 4, (t == 0) ? nullptr : c_all + t * RH,

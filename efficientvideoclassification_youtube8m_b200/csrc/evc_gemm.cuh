@@ -54,6 +54,7 @@ struct GemmArgs {
   int kb_a1;           // k blocks taken from tensor map A1; the remainder comes from A2
   int kb_per_split;
   int debug;           // profiling experiments only (evc_debug_set): 1024 = release the dependent grid at kernel start
+  int stream_k;        // 1: stream-K schedule (see WorkIter) instead of the static (tile, split) round robin
   int segments;        // 1: A*B.  3: split-bf16 "precise" product A_hi*B_hi + A_hi*B_lo + A_lo*B_hi -- the k range is
                        // walked three times into the same f32 accumulator, operands from the hi / lo tensor maps
   // ---- EPI_STORE
@@ -148,6 +149,57 @@ __device__ __forceinline__ void flush_bf16(const float* st, __nv_bfloat16* g, lo
   }
 }
 
+// Work distribution of the persistent kernel.  Every role (producer, MMA, epilogue) of every CTA of a cluster walks
+// the same sequence of work items (tile, slab, k-block range).
+//   classic   item w = cluster_id + i * num_clusters of the tiles x split_k grid: slab = w / tiles, k range = the
+//             split's share.  Rounds over the SMs are quantised: 160 items on 74 clusters take 3 rounds for 2.16
+//             rounds of work.
+//   stream-K  the (tile, k-block) space is cut into num_clusters equal contiguous ranges, one per cluster, so every
+//             cluster issues the same number of MMAs (+-1 k-block).  A range covers the tail of one tile, whole tiles
+//             and the head of another; each piece is an ordinary work item whose partial product goes to slab 0 (the
+//             piece starts at k-block 0) or slab 1 (it does not); a tile that falls entirely into one range is cut in
+//             two so that EVERY tile has exactly one piece per slab -- the consumer sums two slabs, as with split-K 2.
+//             Needs ranges at least one tile long (host checks): then no tile has more than two pieces.
+struct WorkIter {
+  int w, num_work, stride, tiles;
+  long long cursor, end;
+  __device__ __forceinline__ void init(const GemmArgs& a, int cluster_id, int num_clusters, int tiles_) {
+    tiles = tiles_;
+    if (a.stream_k) {
+      const long long units = static_cast<long long>(tiles) * a.kb_total;
+      cursor = units * cluster_id / num_clusters;
+      end = units * (cluster_id + 1) / num_clusters;
+    } else {
+      w = cluster_id;
+      stride = num_clusters;
+      num_work = tiles * a.split_k;
+    }
+  }
+  // false when this cluster has no more work; `last`: this is its final item
+  __device__ __forceinline__ bool next(const GemmArgs& a, int& wt, int& ks, int& kb0, int& kb1, bool& last) {
+    if (a.stream_k) {
+      if (cursor >= end) return false;
+      wt = static_cast<int>(cursor / a.kb_total);
+      kb0 = static_cast<int>(cursor - static_cast<long long>(wt) * a.kb_total);
+      const long long left = end - cursor;
+      kb1 = (left < a.kb_total - kb0) ? kb0 + static_cast<int>(left) : a.kb_total;
+      if (kb0 == 0 && kb1 == a.kb_total) kb1 = a.kb_total >> 1;     // a whole tile: two pieces, one per slab
+      ks = kb0 > 0 ? 1 : 0;
+      cursor += kb1 - kb0;
+      last = cursor >= end;
+      return true;
+    }
+    if (w >= num_work) return false;
+    wt = w % tiles;
+    ks = w / tiles;
+    kb0 = ks * a.kb_per_split;
+    kb1 = min(a.kb_total, kb0 + a.kb_per_split);
+    last = w + stride >= num_work;
+    w += stride;
+    return true;
+  }
+};
+
 // CS = cluster size along M: the CS CTAs of a cluster work on M-adjacent tiles of the same N
 // block, each loads 1/CS of the B tile and multicasts it to all of them (L2 -> SM operand
 // traffic per CTA drops from A+B to A+B/CS; the kernel is L2-bandwidth bound without it).
@@ -212,7 +264,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 
   // work item = CS M-adjacent tiles (one per CTA of the cluster); tiles past tiles_m are all-OOB dummies
   const int tiles_mc = (args.tiles_m + CS - 1) / CS;
-  const int num_work = tiles_mc * args.tiles_n * args.split_k;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -220,17 +271,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       bool released = (args.debug & 1024) != 0;
-      for (int w = cluster_id; w < num_work; w += num_clusters) {
-        if (!released && w + num_clusters >= num_work) {   // last work item of this CTA
+      WorkIter wi;
+      wi.init(args, cluster_id, num_clusters, tiles_mc * args.tiles_n);
+      int wt, ks, kb0, kb1;
+      bool last;
+      while (wi.next(args, wt, ks, kb0, kb1, last)) {
+        if (!released && last) {   // last work item of this CTA
           pdl_launch_dependents();
           released = true;
         }
-        const int wt = w % (tiles_mc * args.tiles_n);
         const int m_blk = (args.n_fastest ? wt / args.tiles_n : wt % tiles_mc) * CS + cta_rank;
         const int n_blk = args.n_fastest ? wt % args.tiles_n : wt / tiles_mc;
-        const int ks = w / (tiles_mc * args.tiles_n);
-        const int kb0 = ks * args.kb_per_split;
-        const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         for (int seg = 0; seg < args.segments; ++seg)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -275,10 +326,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
-        const int ks = w / (tiles_mc * args.tiles_n);
-        const int kb0 = ks * args.kb_per_split;
-        const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+      WorkIter wi;
+      wi.init(args, cluster_id, num_clusters, tiles_mc * args.tiles_n);
+      int wt, ks, kb0, kb1;
+      bool last;
+      for (; wi.next(args, wt, ks, kb0, kb1, last); ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -311,12 +363,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     float* st_f = stage + STG_F32;
     float* st_b0 = stage + STG_BF16;
     int it = 0;
-    for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
-      const int wt = w % (tiles_mc * args.tiles_n);
+    WorkIter wi;
+    wi.init(args, cluster_id, num_clusters, tiles_mc * args.tiles_n);
+    int wt, ks, kb0, kb1;
+    bool last;
+    for (; wi.next(args, wt, ks, kb0, kb1, last); ++it) {
       const int m_blk = (args.n_fastest ? wt / args.tiles_n : wt % tiles_mc) * CS + cta_rank;
       const int n_blk = args.n_fastest ? wt % args.tiles_n : wt / tiles_mc;
-      const int ks = w / (tiles_mc * args.tiles_n);
-      const bool has_acc = min(args.kb_total, (ks + 1) * args.kb_per_split) > ks * args.kb_per_split;
+      const bool has_acc = kb1 > kb0;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;

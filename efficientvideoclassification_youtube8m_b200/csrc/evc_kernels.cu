@@ -506,7 +506,7 @@ __device__ __forceinline__ float moe_class(const float* g, const float* e, int M
   return p;
 }
 
-__global__ void moe_mix_fwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
+__global__ void __launch_bounds__(1024) moe_mix_fwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
                                    long long lde, int V, int M, float* __restrict__ p_out) {
   PDL_PROLOGUE();
   const int b = blockIdx.x;
@@ -594,7 +594,7 @@ __global__ void ce_kl_loss_kernel(const float* __restrict__ P, const float* __re
 // gradients w.r.t. the gate / expert logits in ONE launch per model (one block per video).
 //   pass 1: p[c] (written, kept in L2) and, for the KL normalisers, sum p and sum pT
 //   pass 2: CE/KL terms, dp = ce_scale*dCE/dp + kl_scale*dKL/dp, dG/dE (bf16 GEMM operands)
-__global__ void moe_mix_loss_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
+__global__ void __launch_bounds__(1024) moe_mix_loss_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ E,
                                     long long lde, const float* __restrict__ PT,
                                     const uint8_t* __restrict__ labels, int V, int M, float ce_scale,
                                     float kl_scale, float* __restrict__ P, float* __restrict__ ce_rows,
@@ -1100,7 +1100,7 @@ extern "C" int evc_moe_mix_fwd(const float* G, long long ldg, const float* E, lo
                                float* p_out, void* stream) {
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix: 1 <= num_mixtures <= 8");
   if (B <= 0) return EVC_OK;
-  pdl_launch(moe_mix_fwd_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, V, M, p_out);
+  pdl_launch(moe_mix_fwd_kernel, dim3(B), dim3(1024), 0, EVC_STREAM(stream), G, ldg, E, lde, V, M, p_out);
   count_launch();
   return check_launch("moe_mix_fwd");
 }
@@ -1134,7 +1134,9 @@ extern "C" int evc_moe_mix_loss(const float* G, long long ldg, const float* E, l
   if (M < 1 || M > 8) return set_error(EVC_ERR_UNSUPPORTED, "moe_mix_loss: 1 <= num_mixtures <= 8");
   if (labels == nullptr || ce_rows == nullptr) return set_error(EVC_ERR_ARG, "moe_mix_loss: labels and ce_rows required");
   if (B <= 0) return EVC_OK;
-  pdl_launch(moe_mix_loss_kernel, dim3(B), dim3(256), 0, EVC_STREAM(stream), G, ldg, E, lde, PT, labels, V, M, ce_scale,
+  // one block per video, 1024 threads: with 256 videos the grid is only 1.7 blocks per SM, so the parallelism has to
+  // come from inside the block (measured 70 us -> see profiles/r02 at 256 threads: latency-bound at 16 warps per SM)
+  pdl_launch(moe_mix_loss_kernel, dim3(B), dim3(1024), 0, EVC_STREAM(stream), G, ldg, E, lde, PT, labels, V, M, ce_scale,
              kl_scale, P, ce_rows, kl_rows, static_cast<__nv_bfloat16*>(dG), lddg, static_cast<__nv_bfloat16*>(dE), ldde,
              static_cast<__nv_bfloat16*>(dG_lo), static_cast<__nv_bfloat16*>(dE_lo));
   count_launch();

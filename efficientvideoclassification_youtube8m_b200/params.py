@@ -218,7 +218,7 @@ class HLstmParams:
 
     def apply_gradients_sharded(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
                                 rank: int, world: int, group=None, beta1: float = 0.9, beta2: float = 0.999,
-                                eps: float = 1e-8, gather: bool = True):
+                                eps: float = 1e-8, gather: bool = True, norm_group=None):
         """Same update as apply_gradients for the rows this rank owns.  Expects the matrix gradients
         reduce-scattered (owned rows = average over ranks) and the bias gradients all-reduced.  Returns the
         async all-gather handles of the bf16 operand copies (wait before the next forward)."""
@@ -237,8 +237,9 @@ class HLstmParams:
             w = self.w[n][r0:r1] if n in reg else None
             ops.sumsq(self.g[n][r0:r1], w, wd, self.normsq[i:i + 1], self.wsq[i:i + 1] if w is not None else None)
         # per-variable norms need the other ranks' row blocks: two tiny SUM all-reduces (11 floats each)
-        dist.all_reduce(self.normsq, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(self.wsq, op=dist.ReduceOp.SUM, group=group)
+        ng = norm_group if norm_group is not None else group
+        dist.all_reduce(self.normsq, op=dist.ReduceOp.SUM, group=ng)
+        dist.all_reduce(self.wsq, op=dist.ReduceOp.SUM, group=ng)
         for n in self.vector_names():
             i = idx[n]
             ops.sumsq(self.g[n], None, 0.0, self.normsq[i:i + 1], None)

@@ -83,6 +83,14 @@ class _Base:
         self._dp_ablate = int(os.environ.get("EVC_DP_ABLATE", "0"))
         # optimizer sharding over the data-parallel ranks (on by default when there is more than one)
         self.shard_optimizer = shard_optimizer if shard_optimizer is not None else (self._world() > 1)
+        # The sharded optimizer completes its per-variable norms with two 11-float all-reduces.  On the default
+        # communicator they would queue behind every gradient reduce-scatter issued so far (one NCCL stream per
+        # communicator), i.e. the teacher's optimizer pass would wait for the student's gradients: they get their
+        # own communicator.  (Collective: every rank constructs its trainers in the same order.)
+        self.norm_group = None
+        if self.shard_optimizer and self._world() > 1 and dist.get_backend() == "nccl" \
+                and os.environ.get("EVC_NORM_GROUP", "1") != "0":
+            self.norm_group = dist.new_group()
 
     @staticmethod
     def _world():
@@ -166,7 +174,7 @@ class _Base:
         if n > 1 and self.shard_optimizer and dist.get_backend() == "nccl":
             self._gathers.setdefault(id(params), []).extend(
                 params.apply_gradients_sharded(self.lr, self.clip, self.penalty, dist.get_rank(), n,
-                                               gather=not (self._dp_ablate & 2)))
+                                               gather=not (self._dp_ablate & 2), norm_group=self.norm_group))
         else:
             params.apply_gradients(self.lr, self.clip, self.penalty)
 

@@ -64,9 +64,12 @@ def _lstm_ref(x, W, b, seq_len, T, H, dtype=torch.float64):
 
 
 @pytest.mark.parametrize("use_ws", [False, True])
-@pytest.mark.parametrize("rows,Kx,H,T", [(200, 128, 128, 5), (256, 1152, 1024, 3), (1300, 256, 128, 4)])
+@pytest.mark.parametrize("rows,Kx,H,T", [(200, 128, 128, 5), (256, 1152, 1024, 3), (1300, 256, 128, 4),
+                                         (5120, 1152, 1024, 2), (19000, 128, 256, 3)])
 def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
-    """use_ws=False: fused-epilogue kernels; True: split-K GEMM + cell kernels (fwd only for <=1024 rows)."""
+    """use_ws=False: fused-epilogue kernels; True: split-K GEMM + cell kernels (fwd only for <=1024 rows).
+    The last two shapes have more dgrad tiles than SM pairs: with a workspace the recurrent dgrad runs on the
+    stream-K schedule (5120 x 1024: the teacher's RNN_L1 at B = 256; 19000 x 256: ragged last tile, one N tile)."""
     from efficientvideoclassification_youtube8m_b200 import ops
     torch.manual_seed(0)
     dev = "cuda"
