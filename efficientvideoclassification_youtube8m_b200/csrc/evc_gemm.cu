@@ -114,7 +114,17 @@ static int make_tmap_steps(CUtensorMap* m, const void* ptr, uint64_t inner, uint
 constexpr int kCluster = 2;   // CTAs per cluster sharing a multicast B tile
 static int g_debug = 0;       // profiling experiments only (evc_debug_set)
 
-template <int A_MN, int B_MN, int BN, int EPI, int CS>
+// EVC_PAIR=0: multicast pairs (two 128-row MMAs sharing a multicast B tile) instead of cta_group::2 (A/B experiment)
+static bool pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVC_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+template <int A_MN, int B_MN, int BN, int EPI, int CS, int PAIR = 0>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c,
                   const GemmArgs& args_in, cudaStream_t stream, const CUtensorMap* a1lo = nullptr,
                   const CUtensorMap* a2lo = nullptr, const CUtensorMap* blo = nullptr) {
@@ -123,8 +133,8 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   const CUtensorMap& xa1 = a1lo ? *a1lo : a1;
   const CUtensorMap& xa2 = a2lo ? *a2lo : (a1lo ? *a1lo : a2);
   const CUtensorMap& xb = blo ? *blo : b;
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, CS>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, CS, PAIR>;
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles_mc = (args.tiles_m + CS - 1) / CS;
   const int work = tiles_mc * args.tiles_n * args.split_k;
@@ -257,6 +267,9 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
     if (cs == 1)                                                                                  \
       return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream, pa, pa2, pb)           \
                        : launch<AM, BMN, 128, EPI_STORE, 1>(ta, ta2, tb, tc, g, stream, pa, pa2, pb);          \
+    if (pair_mode())                                                                              \
+      return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster, 1>(ta, ta2, tb, tc, g, stream, pa, pa2, pb) \
+                       : launch<AM, BMN, 128, EPI_STORE, kCluster, 1>(ta, ta2, tb, tc, g, stream, pa, pa2, pb);\
     return bn == 256 ? launch<AM, BMN, 256, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream, pa, pa2, pb)      \
                      : launch<AM, BMN, 128, EPI_STORE, kCluster>(ta, ta2, tb, tc, g, stream, pa, pa2, pb);     \
   }
@@ -401,7 +414,8 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
     g.h_out = hb + (t + 1) * RH;
     g.gates = gb ? gb + t * RH * 4 : nullptr;
     rc = (cs == 1) ? launch<0, 1, 256, EPI_LSTM_FWD, 1>(ta1, ta2, tb, tb, g, stream)
-                   : launch<0, 1, 256, EPI_LSTM_FWD, kCluster>(ta1, ta2, tb, tb, g, stream);
+         : pair_mode() ? launch<0, 1, 256, EPI_LSTM_FWD, kCluster, 1>(ta1, ta2, tb, tb, g, stream)
+                       : launch<0, 1, 256, EPI_LSTM_FWD, kCluster>(ta1, ta2, tb, tb, g, stream);
     if (rc) return rc;
   }
   return EVC_OK;

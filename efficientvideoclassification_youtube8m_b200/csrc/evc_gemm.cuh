@@ -85,12 +85,16 @@ struct GemmArgs {
   __nv_bfloat16* dz_out;        // [M,4H]
 };
 
-template <int BN>
+// PAIR = 1: cta_group::2 -- the two CTAs of a cluster execute one 256 x BN MMA; each keeps its 128 rows of A and
+// HALF of the B tile (its BN/2 columns), so a stage is 16 + 16 KB instead of 16 + 32 KB at BN = 256 and the bytes an SM
+// pulls from the L2 per FLOP drop by a third (ncu, round 2: the 128 x 256 single-CTA tiles of the recurrence GEMMs
+// ran at 62-66 % tensor-pipe activity with the MMA thread waiting for operands -- L2 -> SM traffic 11-13 TB/s).
+template <int BN, int PAIR = 0>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int ACC_STAGES = 2;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   // per epilogue warp 8 KB (1024-byte aligned): two 32x32-word TMA store boxes (plain GEMM), or the
@@ -203,14 +207,15 @@ struct WorkIter {
 // CS = cluster size along M: the CS CTAs of a cluster work on M-adjacent tiles of the same N
 // block, each loads 1/CS of the B tile and multicasts it to all of them (L2 -> SM operand
 // traffic per CTA drops from A+B to A+B/CS; the kernel is L2-bandwidth bound without it).
-template <int A_MN, int B_MN, int BN, int EPI, int CS>
+template <int A_MN, int B_MN, int BN, int EPI, int CS, int PAIR = 0>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
             const __grid_constant__ CUtensorMap tmA1lo, const __grid_constant__ CUtensorMap tmA2lo,
             const __grid_constant__ CUtensorMap tmBlo, const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!PAIR || (CS == 2 && EPI != EPI_LSTM_BWD), "CTA pairs: clusters of two, store / LSTM-forward epilogues");
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -239,15 +244,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CS);   // every CTA of the cluster must have consumed the slot
+      // multicast pairs: every CTA of the cluster must have consumed the slot (each commits to all);
+      // cta_group::2: the leader's single commit frees the slot in both CTAs
+      mbar_init(&empty_bar[i], PAIR ? 1 : CS);
     }
     for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EpiCfg<EPI>::WARPS);
+      // cta_group::2: the epilogue warps of BOTH CTAs release the accumulator stage on the leader's barrier
+      mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * EpiCfg<EPI>::WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
   if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast reaches them
   else __syncthreads();
@@ -287,12 +298,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const bool first = kb < args.kb_a1;
           // segment 0: hi*hi, 1: hi*lo, 2: lo*hi
           const CUtensorMap* ta = (seg == 2) ? (first ? &tmA1lo : &tmA2lo) : (first ? &tmA1 : &tmA2);
           const CUtensorMap* tb = (seg == 1) ? &tmBlo : &tmB;
           const int ka = (first ? kb : kb - args.kb_a1) * BK;
+          if constexpr (PAIR) {
+            // both CTAs load into their own shared memory; all bytes are counted on the LEADER's barrier, which the
+            // leader arms for the pair's 2 x STAGE_BYTES (a peer's bytes may land first: the count is signed)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (A_MN) {
+              tma_load_2d_2sm(sa, ta, &full_bar[stage], m_blk * BM, ka);
+              tma_load_2d_2sm(sa + 8192, ta, &full_bar[stage], m_blk * BM + 64, ka);
+            } else {
+              tma_load_2d_2sm(sa, ta, &full_bar[stage], ka, m_blk * BM);
+            }
+            const int kbk2 = kb * BK;
+            if (B_MN) {
+              constexpr int NBH = BN / 128;        // 64-column boxes of this CTA's half of the B tile
+#pragma unroll
+              for (int j = 0; j < NBH; ++j) {
+                const int i = cta_rank * NBH + j;
+                const int n = (EPI == EPI_LSTM_FWD) ? (i * args.H + n_blk * 64) : (n_blk * BN + i * 64);
+                tma_load_2d_2sm(sb + j * 8192, tb, &full_bar[stage], n, kbk2);
+              }
+            } else {
+              tma_load_2d_2sm(sb, tb, &full_bar[stage], kbk2, n_blk * BN + cta_rank * (BN / 2));
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (A_MN) {
             tma_load_2d(sa, ta, &full_bar[stage], m_blk * BM, ka);
             tma_load_2d(sa + 8192, ta, &full_bar[stage], m_blk * BM + 64, ka);
@@ -321,8 +357,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && (!PAIR || cta_rank == 0)) {     // cta_group::2: the leader issues for the pair
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -346,13 +382,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (seg > 0 || kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_2sm(d_tmem, da, db, idesc, (seg > 0 || kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (seg > 0 || kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CS > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+          if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], kMcMask);
+          else if (CS > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (kb1 > kb0) umma_commit(&tfull_bar[as]);
+        if (PAIR) umma_commit_2sm_mc(&tfull_bar[as], kMcMask);    // the accumulators of both CTAs are complete
+        else if (kb1 > kb0) umma_commit(&tfull_bar[as]);
         else mbar_arrive(&tfull_bar[as]);
       }
     }
@@ -747,7 +786,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       // release the accumulator stage to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
@@ -756,7 +798,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

@@ -194,6 +194,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster (ranks 0 and 1 = the two SMs of a TPC) execute ONE 256 x N MMA: each holds its 128 rows of A
+// and HALF of the B tile in its own shared memory and its 128 accumulator rows in its own TMEM; the instruction is
+// issued by the leader (rank 0) only.  Shared-memory addresses of the pair differ in bit 24 of the shared::cluster
+// window, so "the leader's barrier at my offset" is my address with that bit cleared.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & kPeerBitMask; }
+
+// TMA load into THIS CTA's shared memory whose bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_addr(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the leader's barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B over the pair: M = 256 (128 rows per CTA), B halves from both CTAs
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` when the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 format, version = 1), SWIZZLE_128B.
 // K-major : rows of 128 B (64 bf16 of K); 8-row groups 1024 B apart (SBO); LBO unused.

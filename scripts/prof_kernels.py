@@ -10,6 +10,7 @@ between cudaProfilerStart/Stop so that ncu only sees (and replays) those launche
   fwd    forward of RNN_L1 cell 0 (15 fused GEMM + cell-epilogue steps)
   adam   the teacher's clip + Adam pass (11 sumsq + 11 clip_adam launches)
   head   MoE logit GEMMs + the fused classifier-head kernel + its backward GEMMs
+  rec    forward of RNN_L2 cell 0 (256 rows x 20 steps): the resident-weights persistent recurrence
 """
 import os
 import sys
@@ -42,6 +43,8 @@ elif piece == "wgrad":
     t._cell_dx(b, 0, 1, H, t.dx_l1)
 elif piece == "fwd":
     t._cell_fwd(a, t.x, t.R1 * D, D, 0, 0, t.len_l1)
+elif piece == "rec":
+    t._cell_fwd(t.l2[0], t.l2_in, B * S, S, 1, 0, t.len_l2)
 elif piece == "adam":
     tr.teacher.apply_gradients(tr.lr, tr.clip, tr.penalty)
 elif piece == "head":
