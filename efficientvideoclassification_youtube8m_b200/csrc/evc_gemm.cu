@@ -181,7 +181,7 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   int bn = force_bn ? force_bn : ((N > 128) ? 256 : 128);
   // weight-streaming regime (few rows, wide N: the MoE logits GEMMs, 256 x 9432 x 4096): 128 x 256 tiles give fewer
   // work items than SMs (74 of 148) and stream the weights at a fraction of the HBM rate; 128-wide tiles fill the chip
-  if (!force_bn && bn == 256 && split_k <= 1 &&
+  if (!force_bn && bn == 256 && split_k <= 1 && M <= 2 * BM && K <= 8192 &&
       static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 256) < num_sms() &&
       static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 128) > static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 256))
     bn = 128;

@@ -367,10 +367,12 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ z_part, int S, lo
 // BasicLSTMCell backward at step t: dh = sum_s dh_part[s] (= dz_{t+1} Wh^T) + dh_ext + pass-through;
 // gate gradients dz_t (bf16), carried dc, masked pass-through, and the bias gradient db += column sums of dz_t
 // (nullable; fused here so that dz is not read a second time by a column-sum pass).
-// Block = 8 rows x 32 unit-quads (128 units of one column block); blockIdx.x = column block, blockIdx.y strides
-// over groups of 8 rows, so a thread keeps the column sums of its 16 gate columns in registers over all its rows
-// and the block issues 512 atomics at the end.
-__global__ void __launch_bounds__(256)
+// Block = 8 rows x 32 unit-quads (128 units of one column block), one (row, quad) per thread -- the full-occupancy
+// shape that moves 36 B per element at HBM rate; the 8 rows of a block are summed through shared memory and the
+// block issues 512 warp-coalesced float atomics (16 per warp).  (A grid-stride variant that kept the sums in
+// registers over ~9 rows per thread ran at 3.0 instead of 5.2 TB/s: half the occupancy, no loads in flight across
+// iterations.)
+__global__ void __launch_bounds__(256, 5)
 lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_stride,
                      const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_prev,
                      const float* __restrict__ dh_ext, long long ld_dh_ext,
@@ -385,13 +387,11 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
   __shared__ float red[8][4][132];               // [row lane][gate][128 units + pad]
   const int ql = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int u = (blockIdx.x * 32 + ql) * 4;      // first of this thread's 4 units
-  float bsum[4][4];
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) bsum[g][k] = 0.f;
-  for (int r = blockIdx.y * 8 + rl; r < rows; r += gridDim.y * 8) {
+  const int r = blockIdx.y * 8 + rl;
+  bool contributes = false;
+  if (r < rows) {
     const long long off = static_cast<long long>(r) * H + u;
+    const long long zoff = static_cast<long long>(r) * 4 * H + u;
     const int len = seq_len[r];
     const bool live = t < len;
     float dh[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -411,64 +411,62 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
       const float4 a = *reinterpret_cast<const float4*>(dc_in + static_cast<long long>(r) * ld_dc_in + u);
       dc[0] = a.x; dc[1] = a.y; dc[2] = a.z; dc[3] = a.w;
     }
-    __nv_bfloat16* zp = dz_out + static_cast<long long>(r) * 4 * H + u;
-    const long long zoff = static_cast<long long>(r) * 4 * H + u;
     if (!live) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<uint2*>(zp + g * H) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(dz_out + zoff + g * H) = make_uint2(0u, 0u);
         if (dz_lo != nullptr) *reinterpret_cast<uint2*>(dz_lo + zoff + g * H) = make_uint2(0u, 0u);
       }
       *reinterpret_cast<float4*>(dc_out + off) = make_float4(dc[0], dc[1], dc[2], dc[3]);
       *reinterpret_cast<float4*>(dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
-      continue;
-    }
-    float gi[4], gj[4], gf[4], go[4], cp[4] = {0.f, 0.f, 0.f, 0.f};
-    load4_split(gates, gates_lo, zoff + 0 * H, gi);
-    load4_split(gates, gates_lo, zoff + 1 * H, gj);
-    load4_split(gates, gates_lo, zoff + 2 * H, gf);
-    load4_split(gates, gates_lo, zoff + 3 * H, go);
-    if (c_prev != nullptr) {
-      const float4 a = *reinterpret_cast<const float4*>(c_prev + off);
-      cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w;
-    }
-    float dz[4][4], dco[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float cn = cp[k] * gf[k] + gi[k] * gj[k];
-      const float tc = tanh_(cn);
-      const float dcn = dc[k] + dh[k] * go[k] * (1.f - tc * tc);
-      dz[0][k] = dcn * gj[k] * gi[k] * (1.f - gi[k]);
-      dz[1][k] = dcn * gi[k] * (1.f - gj[k] * gj[k]);
-      dz[2][k] = dcn * cp[k] * gf[k] * (1.f - gf[k]);
-      dz[3][k] = dh[k] * tc * go[k] * (1.f - go[k]);
-      dco[k] = dcn * gf[k];
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint2 packed = pack4_bf16(dz[g][0], dz[g][1], dz[g][2], dz[g][3]);
-      *reinterpret_cast<uint2*>(zp + g * H) = packed;
-      // the bias gradient sums the values the weight-gradient GEMMs see: the bf16-rounded dz (+ its residual plane)
-      float q[4];
-      unpack4_bf16(packed, q);
-      if (dz_lo != nullptr) {
-        const uint2 pl = pack4_bf16(dz[g][0] - q[0], dz[g][1] - q[1], dz[g][2] - q[2], dz[g][3] - q[3]);
-        *reinterpret_cast<uint2*>(dz_lo + zoff + g * H) = pl;
-        float ql[4];
-        unpack4_bf16(pl, ql);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) q[k] += ql[k];
+    } else {
+      float gi[4], gj[4], gf[4], go[4], cp[4] = {0.f, 0.f, 0.f, 0.f};
+      load4_split(gates, gates_lo, zoff + 0 * H, gi);
+      load4_split(gates, gates_lo, zoff + 1 * H, gj);
+      load4_split(gates, gates_lo, zoff + 2 * H, gf);
+      load4_split(gates, gates_lo, zoff + 3 * H, go);
+      if (c_prev != nullptr) {
+        const float4 a = *reinterpret_cast<const float4*>(c_prev + off);
+        cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w;
       }
+      float dz[4][4], dco[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) bsum[g][k] += q[k];
+      for (int k = 0; k < 4; ++k) {
+        const float cn = cp[k] * gf[k] + gi[k] * gj[k];
+        const float tc = tanh_(cn);
+        const float dcn = dc[k] + dh[k] * go[k] * (1.f - tc * tc);
+        dz[0][k] = dcn * gj[k] * gi[k] * (1.f - gi[k]);
+        dz[1][k] = dcn * gi[k] * (1.f - gj[k] * gj[k]);
+        dz[2][k] = dcn * cp[k] * gf[k] * (1.f - gf[k]);
+        dz[3][k] = dh[k] * tc * go[k] * (1.f - go[k]);
+        dco[k] = dcn * gf[k];
+      }
+      contributes = dbias != nullptr;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint2 packed = pack4_bf16(dz[g][0], dz[g][1], dz[g][2], dz[g][3]);
+        *reinterpret_cast<uint2*>(dz_out + zoff + g * H) = packed;
+        // the bias gradient sums the values the weight-gradient GEMMs see: the bf16-rounded dz (+ its residual plane)
+        float q[4];
+        unpack4_bf16(packed, q);
+        if (dz_lo != nullptr) {
+          const uint2 pl = pack4_bf16(dz[g][0] - q[0], dz[g][1] - q[1], dz[g][2] - q[2], dz[g][3] - q[3]);
+          *reinterpret_cast<uint2*>(dz_lo + zoff + g * H) = pl;
+          float ql4[4];
+          unpack4_bf16(pl, ql4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] += ql4[k];
+        }
+        if (dbias != nullptr) *reinterpret_cast<float4*>(&red[rl][g][ql * 4]) = make_float4(q[0], q[1], q[2], q[3]);
+      }
+      *reinterpret_cast<float4*>(dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
     }
-    *reinterpret_cast<float4*>(dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
   }
   if (dbias == nullptr) return;
+  if (!contributes) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) red[rl][g][ql * 4 + k] = bsum[g][k];
+    for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(&red[rl][g][ql * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 512; i += 256) {
     const int g = i >> 7, c = i & 127;
@@ -970,9 +968,8 @@ int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, con
                          const void* gates_lo, void* dz_lo) {
   if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_cell_bwd: H must be a multiple of 128");
   const int col_blocks = H / 128;
-  int row_groups = (rows + 7) / 8;
-  const int cap = (num_sms() * 4 + col_blocks - 1) / col_blocks;     // ~4 resident blocks per SM in one wave
-  if (row_groups > cap) row_groups = cap;
+  const int row_groups = (rows + 7) / 8;
+  if (row_groups > 65535) return set_error(EVC_ERR_UNSUPPORTED, "lstm_cell_bwd: more than 524280 rows");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(col_blocks), static_cast<unsigned>(row_groups));
   cfg.blockDim = dim3(256);

@@ -10,7 +10,11 @@ x, nf, lab = O.synthetic_batch(B, seed=1234, full_length=True)
 tr = TeacherStudentTrainer(ModelConfig(), batch_size=B, device="cuda", base_learning_rate=1e-5)
 xd, nfd, labd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda(), torch.from_numpy(lab).cuda()
 torch.cuda.synchronize()
-for _ in range(steps):
+for _ in range(steps - 1):
     tr.step(xd, nfd, labd)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one warm step is listed
+tr.step(xd, nfd, labd)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print(tr.fetch())
