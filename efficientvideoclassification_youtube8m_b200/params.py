@@ -218,19 +218,27 @@ class HLstmParams:
 
     def apply_gradients_sharded(self, lr: float, clip_gradient_norm: float, regularization_penalty: float,
                                 rank: int, world: int, group=None, beta1: float = 0.9, beta2: float = 0.999,
-                                eps: float = 1e-8, gather: bool = True, norm_group=None):
+                                eps: float = 1e-8, gather: bool = True, norm_group=None, first: int = 0,
+                                last: Optional[int] = None, advance: bool = True):
         """Same update as apply_gradients for the rows this rank owns.  Expects the matrix gradients
         reduce-scattered (owned rows = average over ranks) and the bias gradients all-reduced.  Returns the
-        async all-gather handles of the bf16 operand copies (wait before the next forward)."""
+        async all-gather handles of the bf16 operand copies (wait before the next forward).
+        Variables names[first:last] only (the clip is per variable, so the classifier's tensors can be updated and
+        gathered while the LSTM backward is still running); advance=False after `begin_apply`."""
         import torch.distributed as dist
         wd = float(regularization_penalty) * self.cfg.l2_penalty
-        ops.fill_f32(self.normsq, 0.0)
-        ops.fill_f32(self.wsq, 0.0)
-        ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
+        last = len(self.names) if last is None else last
+        in_range = set(self.names[first:last])
+        ops.fill_f32(self.normsq[first:last], 0.0)
+        ops.fill_f32(self.wsq[first:last], 0.0)
+        if advance:
+            ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
         reg = (self.gates_w, self.experts_w)
         idx = {n: i for i, n in enumerate(self.names)}
         blocks = {}
         for n in self.matrix_names():
+            if n not in in_range:
+                continue
             r0, r1 = self.row_block(n, rank, world)
             blocks[n] = (r0, r1)
             i = idx[n]
@@ -238,13 +246,15 @@ class HLstmParams:
             ops.sumsq(self.g[n][r0:r1], w, wd, self.normsq[i:i + 1], self.wsq[i:i + 1] if w is not None else None)
         # per-variable norms need the other ranks' row blocks: two tiny SUM all-reduces (11 floats each)
         ng = norm_group if norm_group is not None else group
-        dist.all_reduce(self.normsq, op=dist.ReduceOp.SUM, group=ng)
-        dist.all_reduce(self.wsq, op=dist.ReduceOp.SUM, group=ng)
+        dist.all_reduce(self.normsq[first:last], op=dist.ReduceOp.SUM, group=ng)
+        dist.all_reduce(self.wsq[first:last], op=dist.ReduceOp.SUM, group=ng)
         for n in self.vector_names():
+            if n not in in_range:
+                continue
             i = idx[n]
             ops.sumsq(self.g[n], None, 0.0, self.normsq[i:i + 1], None)
         handles = []
-        for n in self.names:
+        for n in self.names[first:last]:
             i = idx[n]
             if n in blocks:
                 r0, r1 = blocks[n]

@@ -182,8 +182,19 @@ class _Base:
     # after classifier_backward, so their clip+Adam pass (HBM-bound) runs on an optimizer stream next to the
     # LSTM backward (tensor-bound) instead of after it.  With several ranks the optimizer is sharded and
     # waits for the collectives instead.
+    def _sharded(self) -> bool:
+        return self._world() > 1 and self.shard_optimizer and dist.get_backend() == "nccl"
+
     def _early_apply_ok(self) -> bool:
-        return self._world() == 1 and bool(overlap_mode() & OVERLAP_OPTIMIZER) and self.device.type == "cuda"
+        """One GPU: only with EVC_OVERLAP bit 8 (measured no gain: the optimizer's HBM traffic slows the power-capped
+        GEMMs it runs next to).  Sharded data parallel: on by default (EVC_EARLY_OPT=0 disables) -- the classifier's
+        tensors are 2/3 of the bytes; updating and all-gathering them during the LSTM backward takes their
+        all-gather (and a rank's 1/N optimizer pass) off the end of the step."""
+        if self.device.type != "cuda":
+            return False
+        if self._sharded():
+            return os.environ.get("EVC_EARLY_OPT", "1") != "0"
+        return self._world() == 1 and bool(overlap_mode() & OVERLAP_OPTIMIZER)
 
     def _opt_stream(self, params):
         st = self._opt_streams.get(id(params))
@@ -199,11 +210,23 @@ class _Base:
         ev.record(cur)
         opt.wait_event(ev)
         with torch.cuda.stream(opt):
-            params.apply_gradients(self.lr, self.clip, self.penalty, first=8, advance=False)
+            self._apply_range(params, 8, None)
+
+    def _apply_range(self, params, first, last):
+        """clip + Adam of names[first:last] on the current stream once their gradient collectives are complete."""
+        if self._sharded():
+            self._finish_allreduce(params)      # (only this range's collectives have been issued so far)
+            self._gathers.setdefault(id(params), []).extend(
+                params.apply_gradients_sharded(self.lr, self.clip, self.penalty, dist.get_rank(), self._world(),
+                                               gather=not (self._dp_ablate & 2), norm_group=self.norm_group,
+                                               first=first, last=last, advance=False))
+        else:
+            self._finish_allreduce(params)
+            params.apply_gradients(self.lr, self.clip, self.penalty, first=first, last=last, advance=False)
 
     def _apply_lstm_late(self, params):
         """The other half of `_apply_classifier_early`, after lstm_backward."""
-        params.apply_gradients(self.lr, self.clip, self.penalty, first=0, last=8, advance=False)
+        self._apply_range(params, 0, 8)
         torch.cuda.current_stream().wait_stream(self._opt_stream(params)[0])
 
     def _finish_gathers(self, params=None):

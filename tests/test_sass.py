@@ -39,9 +39,13 @@ def test_gemm_kernels_use_tcgen05_tmem_and_tma():
         assert "UTMALDG" in k, name                            # cp.async.bulk.tensor loads
         assert "SYNCS.PHASECHK" in k and "SYNCS.ARRIVE" in k, name   # mbarrier pipeline
         assert "HMMA" not in k.replace("UTCHMMA", ""), name    # no legacy mma.sync path
-    # CTA-pair variants multicast the B tile and release slots in both CTAs; plain GEMMs store with TMA
-    pairs = [k for k in gemm if re.match(r"_ZN3evc11gemm_kernelILi\dELi\dELi\d+ELi\dELi2E", k)]
-    assert pairs and all("UTMALDG.2D.MULTICAST" in k and "UTCBAR.MULTICAST" in k for k in pairs)
+    # cluster-of-two variants: multicast pairs (PAIR=0) multicast the B tile and release slots in both CTAs;
+    # cta_group::2 pairs (PAIR=1) issue the 2-CTA forms of the MMA, the TMA loads and the commit
+    mc = [k for k in gemm if re.match(r"_ZN3evc11gemm_kernelILi\dELi\dELi\d+ELi\dELi2ELi0E", k)]
+    assert mc and all("UTMALDG.2D.MULTICAST" in k and "UTCBAR.MULTICAST" in k for k in mc)
+    two = [k for k in gemm if re.match(r"_ZN3evc11gemm_kernelILi\dELi\dELi\d+ELi\dELi2ELi1E", k)]
+    assert len(two) >= 6 and all("UTCHMMA.2CTA" in k and "UTMALDG.2D.2CTA" in k and "UTCBAR.2CTA.MULTICAST" in k
+                                  for k in two), [k.split("\n", 1)[0] for k in two][:3]
     stores = [k for k in gemm if re.match(r"_ZN3evc11gemm_kernelILi\dELi\dELi\d+ELi0E", k)]
     assert stores and all("UTMASTG" in k for k in stores)
 
