@@ -547,15 +547,26 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
   const __nv_bfloat16* gl = static_cast<const __nv_bfloat16*>(gates_lo_all);
   __nv_bfloat16* zl = static_cast<__nv_bfloat16*>(dz_lo_all);
   const __nv_bfloat16* whl = x2 ? static_cast<const __nv_bfloat16*>(W_lo) + static_cast<long long>(Kx) * 4 * H : nullptr;
-  if (dbias != nullptr && workspace == nullptr)
-    return set_error(EVC_ERR_UNSUPPORTED, "lstm_seq_bwd: the bias gradient is fused into the cell kernel of the "
-                                          "workspace path (use evc_colsum_bf16 over dz with the fused-epilogue path)");
+  // Which form of the backward step: (a) split-K / stream-K GEMM into f32 slabs + cell kernel (default with a
+  // workspace), (b) ONE kernel per step whose epilogue is the cell backward (EPI_LSTM_BWD: no slab round trip, no
+  // second launch; the only form without a workspace).  Measured on B200 with cta_group::2 pairs, 8 epilogue warps
+  // and the bias sums fused (round 2, same-call A/B, profiles/r02_pair_ab.txt): (b) makes the joint step 5 % SLOWER
+  // (12.93 vs 12.31 ms) -- 128-wide tiles pull 1.33x the operand bytes per FLOP and the 32 B/element epilogue does
+  // not hide behind a 64-k-block main loop -- so (a) stays the default; EVC_FUSED_BWD=1 selects (b) above 1024 rows.
+  static int fused_default = -1;
+  if (fused_default < 0) {
+    const char* e = getenv("EVC_FUSED_BWD");
+    fused_default = e ? atoi(e) : 0;
+  }
+  // (evc_debug_set bit 2048 forces the slab path, bit 4096 the fused path: tests exercise both in one process)
+  const bool want_fused = workspace == nullptr || (g_debug & 4096) ||
+                          (!(g_debug & 2048) && fused_default != 0 && rows > 1024);
   if (H % 128 != 0) return set_error(EVC_ERR_ARG, "lstm_seq_bwd: H must be a multiple of 128");
   const __nv_bfloat16* gb = static_cast<const __nv_bfloat16*>(gates_all);
   __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(dz_all);
   const __nv_bfloat16* wh = static_cast<const __nv_bfloat16*>(W) + static_cast<long long>(Kx) * 4 * H;
   const long long RH = static_cast<long long>(rows) * H;
-  if (workspace != nullptr) {
+  if (workspace != nullptr && (x2 || !want_fused)) {
     // Recurrent dgrad dh = dz_{t+1} Wh^T as a (split-K) GEMM into f32 slabs + a full-occupancy cell
     // kernel.  Measured faster than the fused epilogue at every row count: the cell backward moves
     // 36 B per element, which 4 epilogue warps per SM cannot keep in flight behind a 4096-deep GEMM.
@@ -597,8 +608,21 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
   CUtensorMap tb;  // B[k = gate column, n = unit] = Wh[unit][gate column] : stored [N][K] = K-major
   int rc = make_tmap_b(&tb, wh, 0, 4LL * H, H, 4 * H, 128, cs);
   if (rc) return rc;
+  if (dbias != nullptr) {
+    cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * 4 * H, stream);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(dbias)");
+  }
   for (int t = T - 1; t >= 0; --t) {
     const bool last = (t == T - 1);
+    if (last && workspace != nullptr) {
+      // no recurrent term at the last step: the stand-alone cell kernel (HBM-bound, no tensor work to fuse with)
+      rc = launch_lstm_cell_bwd(static_cast<const float*>(workspace), 0, RH, gb + t * RH * 4,
+                                (t == 0) ? nullptr : c_all + t * RH, dh_ext_all ? dh_ext_all + t * RH : nullptr, H,
+                                dh_final, ld_dh_final, dc_final, ld_dc_final, seq_len, t, rows, H, zb + t * RH * 4, dc,
+                                dh_pass, dbias, stream);
+      if (rc) return rc;
+      continue;
+    }
     CUtensorMap ta;
     // A = dz_{t+1} [rows, 4H]; at the last step there is no recurrent term (the map is unused)
     rc = make_tmap_a(&ta, zb + (last ? t : t + 1) * RH * 4, 0, 4LL * H, rows, 4 * H);
@@ -624,8 +648,10 @@ extern "C" int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, c
     g.dh_pass_out = dh_pass;
     g.dc_out = dc;
     g.dz_out = zb + t * RH * 4;
+    g.dbias = dbias;
     rc = (cs == 1) ? launch<0, 0, 128, EPI_LSTM_BWD, 1>(ta, ta, tb, tb, g, stream)
-                   : launch<0, 0, 128, EPI_LSTM_BWD, kCluster>(ta, ta, tb, tb, g, stream);
+         : pair_mode() ? launch<0, 0, 128, EPI_LSTM_BWD, kCluster, 1>(ta, ta, tb, tb, g, stream)
+                       : launch<0, 0, 128, EPI_LSTM_BWD, kCluster>(ta, ta, tb, tb, g, stream);
     if (rc) return rc;
   }
   return EVC_OK;

@@ -43,7 +43,7 @@ constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 // therefore runs with TWO warps per TMEM lane quarter (each owns 32 of the tile's 64 units), which share
 // the scheduler and hide each other's latencies; the other epilogues keep one.
 template <int EPI> struct EpiCfg {
-  static constexpr int WARPS = (EPI == EPI_LSTM_FWD) ? 8 : 4;
+  static constexpr int WARPS = (EPI == EPI_LSTM_FWD || EPI == EPI_LSTM_BWD) ? 8 : 4;
   static constexpr int THREADS = 64 + 32 * WARPS;
 };
 
@@ -83,6 +83,7 @@ struct GemmArgs {
   float* dh_pass_out;           // [M,H]
   float* dc_out;                // [M,H]
   __nv_bfloat16* dz_out;        // [M,4H]
+  float* dbias;                 // [4H] += column sums of dz_out (nullable)
 };
 
 // PAIR = 1: cta_group::2 -- the two CTAs of a cluster execute one 256 x BN MMA; each keeps its 128 rows of A and
@@ -215,7 +216,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             const __grid_constant__ CUtensorMap tmBlo, const GemmArgs args) {
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
-  static_assert(!PAIR || (CS == 2 && EPI != EPI_LSTM_BWD), "CTA pairs: clusters of two, store / LSTM-forward epilogues");
+  static_assert(!PAIR || CS == 2, "CTA pairs are clusters of two");
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -683,24 +684,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           __syncwarp();                                     // staging is overwritten by the next chunk
         }
       } else {
-        // EPI_LSTM_BWD: accumulator = dz_{t+1} * Wh^T, columns = hidden units of this tile.  Same scheme:
-        // 32 x 32 accumulator strips are transposed through shared memory, then lane = (row, 4 units).
+        // EPI_LSTM_BWD: accumulator = dz_{t+1} * Wh^T, columns = hidden units of this tile.  32 x 32 accumulator
+        // strips are transposed through shared memory (XOR-swizzled, pitch 32: conflict-free both ways), then
+        // lane = (row, 4 units) and the whole BasicLSTM cell backward runs here: 20 B read + 12 B written per
+        // element, no f32 slab round trip, no second kernel.  Two warps share a TMEM lane quarter and split the
+        // strips (even / odd); all loads of four row iterations are issued before the first is used.  The bias
+        // gradient (column sums of dz) is accumulated per strip: registers -> 2 shuffles over the row lanes ->
+        // 16 atomics per 8 lanes.
         const int H = args.H;
         const int pr = lane >> 3, pc = (lane & 7) * 4;
+        const int wg = (warp - 2) >> 2;                     // which of the two warps of this lane quarter
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int cs0 = 0; cs0 < BN; cs0 += 32) {
+        for (int cs0 = wg * 32; cs0 < BN; cs0 += 64) {
           if (n_blk * BN + cs0 >= H) break;                 // warp-uniform
           if (has_acc) {
             uint32_t racc[32];
             tmem_ld32(taddr + cs0, racc);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(racc[j]);
+            for (int j = 0; j < 32; ++j) stage[lane * 32 + (j ^ lane)] = __uint_as_float(racc[j]);
           }
           __syncwarp();
           const int u = n_blk * BN + cs0 + pc;              // first of this lane's 4 units
+          float bsum[4][4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bsum[g][k] = 0.f;
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
             // phase A: all loads of 4 lane-iterations are issued before any of them is used
@@ -734,8 +746,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               float dh[4] = {dhv[ii].x, dhv[ii].y, dhv[ii].z, dhv[ii].w};
               float dc[4] = {dcv[ii].x, dcv[ii].y, dcv[ii].z, dcv[ii].w};
               if (has_acc) {
-                const float* sp = stage + rl * 33 + pc;
-                dh[0] += sp[0]; dh[1] += sp[1]; dh[2] += sp[2]; dh[3] += sp[3];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dh[k] += stage[rl * 32 + ((pc + k) ^ rl)];
               }
               if (args.t + 1 >= len && args.dh_pass_in != nullptr) {   // masked at step t+1 (or t is the last step)
                 const float4 e = *reinterpret_cast<const float4*>(args.dh_pass_in + static_cast<long long>(r) * args.ld_dh_pass_in + u);
@@ -770,6 +782,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                   __nv_bfloat162 a23 = __floats2bfloat162_rn(dz4[g][2], dz4[g][3]);
                   *reinterpret_cast<uint2*>(zp + g * H) =
                       make_uint2(*reinterpret_cast<uint32_t*>(&a01), *reinterpret_cast<uint32_t*>(&a23));
+                  // the bias gradient sums the values the weight-gradient GEMMs see: the bf16-rounded dz
+                  const float2 q01 = __bfloat1622float2(a01), q23 = __bfloat1622float2(a23);
+                  bsum[g][0] += q01.x; bsum[g][1] += q01.y; bsum[g][2] += q23.x; bsum[g][3] += q23.y;
                 }
                 *reinterpret_cast<float4*>(args.dc_out + off) = make_float4(dco[0], dco[1], dco[2], dco[3]);
               } else {
@@ -779,6 +794,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                 *reinterpret_cast<float4*>(args.dh_pass_out + off) = make_float4(dh[0], dh[1], dh[2], dh[3]);
               }
             }
+          }
+          if (args.dbias != nullptr) {
+            // sum over the 4 row lanes (lane bits 3, 4); lanes 0..7 then hold the 32 rows' sums of their 4 units
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float v = bsum[g][k];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (pr == 0 && v != 0.f) atomicAdd(args.dbias + g * H + u + k, v);
+              }
           }
           __syncwarp();
         }

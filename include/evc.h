@@ -42,9 +42,10 @@ const char* evc_last_error(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 long long evc_launch_count(void);
 
-/* profiling experiments only (bit flags): 128 = plain GEMMs store through the LSU path instead of TMA bulk
+/* profiling experiments and tests only (bit flags): 128 = plain GEMMs store through the LSU path instead of TMA bulk
  * stores, 256 = no programmatic dependent launch for the GEMM kernels, 1024 = release the dependent grid at
- * kernel start instead of at the last tile.  Also settable with the EVC_DEBUG environment variable. */
+ * kernel start instead of at the last tile, 2048 / 4096 = evc_lstm_seq_bwd always takes the slab path / the fused
+ * dgrad + cell-backward kernel.  Also settable with the EVC_DEBUG environment variable. */
 int evc_debug_set(int flags);
 
 /* ---- input: tf.nn.l2_normalize (train.py:256) + uniform gather (train.py:265-272) or
@@ -138,10 +139,11 @@ int evc_lstm_seq_fwd_resident(const void* x, long long x_step_stride, int Kx, co
  * epilogue, the gate gradients dz_t (bf16 [T,rows,4H]) with the sequence_length mask.
  * dh_ext_all f32 [T,rows,H] (nullable): gradient w.r.t. the cell output at each step (from the cell
  * above).  dh_final/dc_final (nullable, row pitches ld_*): gradient w.r.t. the final state.
- * dh_pass, dc: f32 [rows,H] scratch.  With a workspace the recurrent dgrad runs as a (split-K) GEMM
- * + a full-occupancy cell kernel (measured faster); NULL selects the fused-epilogue kernel.
- * dbias f32 [4H] (nullable, workspace path only): the bias gradient = column sums of dz over all steps and rows,
- * accumulated by the cell kernel while it writes dz (zeroed by this call). */
+ * dh_pass, dc: f32 [rows,H] scratch.  Two forms of a step: ONE kernel whose epilogue is the cell backward (no
+ * workspace needed; the default above 1024 rows), or a split-K / stream-K GEMM into f32 slabs in `workspace` + a
+ * full-occupancy cell kernel (small row counts, and always in split-bf16 mode).
+ * dbias f32 [4H] (nullable): the bias gradient = column sums of dz over all steps and rows, accumulated by the
+ * kernel that writes dz (zeroed by this call). */
 int evc_lstm_seq_bwd(const void* W, int Kx, int rows, int H, int T, const int* seq_len, const void* gates_all,
                      const float* c_all, const float* dh_ext_all, const float* dh_final, long long ld_dh_final,
                      const float* dc_final, long long ld_dc_final, float* dh_pass, float* dc, void* dz_all,

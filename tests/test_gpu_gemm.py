@@ -63,16 +63,28 @@ def _lstm_ref(x, W, b, seq_len, T, H, dtype=torch.float64):
     return c, h, torch.stack(hs)
 
 
-@pytest.mark.parametrize("use_ws", [False, True])
+@pytest.mark.parametrize("use_ws", [False, True, "fused"])
 @pytest.mark.parametrize("rows,Kx,H,T", [(200, 128, 128, 5), (256, 1152, 1024, 3), (1300, 256, 128, 4),
                                          (5120, 1152, 1024, 2), (19000, 128, 256, 3)])
 def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
-    """use_ws=False: fused-epilogue kernels; True: split-K GEMM + cell kernels (fwd only for <=1024 rows).
+    """use_ws=False: fused-epilogue kernels (forward: GEMM + cell epilogue; backward: dgrad GEMM + cell-backward
+    epilogue); True: forward slab path for <=1024 rows, backward slab path (split-K / stream-K GEMM + cell kernel with
+    fused bias sums); "fused": workspace present but the fused backward kernel forced (cta_group::2 pairs above 128 rows,
+    last step through the stand-alone cell kernel).
     The last two shapes have more dgrad tiles than SM pairs: with a workspace the recurrent dgrad runs on the
     stream-K schedule (5120 x 1024: the teacher's RNN_L1 at B = 256; 19000 x 256: ragged last tile, one N tile)."""
-    from efficientvideoclassification_youtube8m_b200 import ops
+    from efficientvideoclassification_youtube8m_b200 import _lib, ops
     torch.manual_seed(0)
     dev = "cuda"
+    if use_ws == "fused":         # with a workspace, force the fused dgrad + cell-backward kernel (default: slab path)
+        _lib.lib.evc_debug_set(4096)
+    try:
+        _lstm_seq_fwd_bwd_body(ops, rows, Kx, H, T, bool(use_ws), dev)
+    finally:
+        _lib.lib.evc_debug_set(0)
+
+
+def _lstm_seq_fwd_bwd_body(ops, rows, Kx, H, T, use_ws, dev):
     ws = torch.empty(ops.lstm_workspace_bytes(rows, H, Kx), dtype=torch.uint8, device=dev) if use_ws else None
     x = (torch.randn(T, rows, Kx, device=dev) * 0.5).to(torch.bfloat16)
     W = (torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)).to(torch.bfloat16)
@@ -105,9 +117,9 @@ def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
     dh_pass = torch.zeros(rows, H, device=dev)
     dc = torch.zeros(rows, H, device=dev)
     dh_ext_masked = torch.where(live_all, dh_ext, torch.zeros_like(dh_ext)).contiguous()
-    # workspace path: the bias gradient is accumulated by the cell kernel while it writes dz (pre-filled with
-    # garbage: the call zeroes it)
-    db_fused = torch.full((4 * H,), 7.0, device=dev) if use_ws else None
+    # the bias gradient is accumulated by the kernel that writes dz -- the cell kernel of the slab path or the fused
+    # dgrad + cell-backward epilogue (pre-filled with garbage: the call zeroes it)
+    db_fused = torch.full((4 * H,), 7.0, device=dev)
     ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc, dz, ws,
                      dbias=db_fused)
     # wgrad: dW = [x | h_prev]^T dz ; dX = dz Wx^T ; db = colsum dz
@@ -126,13 +138,9 @@ def test_lstm_seq_fwd_bwd(rows, Kx, H, T, use_ws):
     assert rel(dW, gW) < 3e-2, rel(dW, gW)
     assert rel(dX.view(T, rows, Kx), gx) < 3e-2, rel(dX.view(T, rows, Kx), gx)
     assert rel(db, gb) < 3e-2, rel(db, gb)
-    if use_ws:      # same sums of the same bf16 values, only the float summation order differs
-        assert rel(db_fused, gb) < 3e-2
-        assert (db_fused - db).abs().max().item() <= 1e-4 * db.abs().max().item() + 1e-6
-    else:
-        with pytest.raises(Exception, match="bias gradient"):
-            ops.lstm_seq_bwd(W, Kx, rows, H, T, seq_len, gates, c_all, dh_ext_masked, dh_f, H, dc_f, H, dh_pass, dc,
-                             dz, None, dbias=db)
+    # same sums of the same bf16 values, only the float summation order differs
+    assert rel(db_fused, gb) < 3e-2
+    assert (db_fused - db).abs().max().item() <= 1e-4 * db.abs().max().item() + 1e-6
 
 
 @pytest.mark.parametrize("rows,Kx,H,T,train", [(256, 4096, 1024, 6, True), (1280, 1152, 1024, 6, True),
