@@ -2,6 +2,7 @@
 // points evc_gemm_bf16 / evc_lstm_seq_fwd / evc_lstm_seq_bwd declared in include/evc.h.
 #include "evc_gemm.cuh"
 #include "evc_rec.cuh"
+#include "evc_cluster.cuh"
 #include "evc_host.h"
 
 #include <cudaTypedefs.h>
@@ -336,6 +337,52 @@ extern "C" long long evc_lstm_workspace_bytes(int rows, int H, int Kx, int preci
   return (f > b ? f : b) + 256;
 }
 
+// ------------------------------------------------------------------ cluster split-K step (csrc/evc_cluster.cuh)
+// Number of K splits (= cluster size) for a small-row step, 0 = not eligible: the tiles x KS CTAs should fit one wave.
+// OFF by default (EVC_CLUSTER_STEP=1 or evc_debug_set bit 16384 enables it): measured on B200 at 256 rows it takes 19.7 /
+// 15.7 us per step (Kx = 4096 / 1024) against 18.4 / 14.5 us for the slab path -- both stream the whole weight matrix
+// from the L2 once per 128-row tile and step (84 MB at Kx = 4096), which is what bounds them; the DSMEM exchange
+// (96 KB per CTA + two cluster barriers) costs as much as the slab round trip it removes
+// (profiles/r02_resident_recurrence.md).  Only keeping the weights resident (evc_rec.cuh: 9.3 us per step) helps.
+static int cluster_step_splits(int rows, int H, int Kx) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("EVC_CLUSTER_STEP");
+    enabled = e ? atoi(e) : 0;
+  }
+  if (!(enabled || (g_debug & 16384)) || (g_debug & 8192) || H % 64 != 0 || Kx % BK != 0) return 0;
+  const int tiles = ceil_div(rows, BM) * (H / 64);
+  int ks = 8;
+  while (ks >= 2 && tiles * ks > num_sms()) ks >>= 1;
+  while (ks >= 2 && Kx / BK < 2 * ks) ks >>= 1;      // at least two k blocks per CTA at t = 0
+  return ks >= 2 ? ks : 0;
+}
+
+template <int KS>
+static int launch_cluster_step(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
+                               const ClusterStepArgs& args, cudaStream_t stream) {
+  auto kern = lstm_cluster_step_fwd_kernel<KS>;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(kern), CL_SMEM_BYTES)) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(args.tiles_m * args.tiles_n * KS));
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = CL_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = KS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, b, args);
+  count_launch();
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(lstm_cluster_step_fwd_kernel)");
+  return check_launch("lstm_cluster_step_fwd_kernel");
+}
+
 // Steps [t_begin, t_end) of the same layer: lets the host interleave the two cells of a MultiRNNCell on two
 // streams (cell 1 step t only needs cell 0 step t), so that the SMs one kernel leaves idle in its last round
 // over the tiles are taken by the other cell's kernel.
@@ -361,6 +408,35 @@ extern "C" int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, in
   __nv_bfloat16* gb = static_cast<__nv_bfloat16*>(gates_all);
   const long long RH = static_cast<long long>(rows) * H;
   int rc;
+  if (const int ksplit = (!x2 && rows <= 1024) ? cluster_step_splits(rows, H, Kx) : 0) {
+    // Small-row steps as ONE kernel each: split-K over a cluster, partial sums through DSMEM, cell update fused
+    CUtensorMap tbw;
+    rc = make_tmap_b(&tbw, W, 1, 4LL * H, 4 * H, Kx + H, 256, 1);
+    if (rc) return rc;
+    for (int t = t_begin; t < t_end; ++t) {
+      CUtensorMap ta1, ta2;
+      rc = make_tmap_a(&ta1, xb + t * x_step_stride, 0, Kx, rows, Kx);
+      if (rc) return rc;
+      rc = make_tmap_a(&ta2, hb + t * RH, 0, H, rows, H);
+      if (rc) return rc;
+      ClusterStepArgs a = {};
+      a.rows = rows; a.H = H; a.t = t;
+      a.tiles_m = ceil_div(rows, BM); a.tiles_n = H / 64;
+      a.kb_a1 = Kx / BK;
+      a.kb_total = a.kb_a1 + (t == 0 ? 0 : H / BK);
+      a.bias = bias; a.seq_len = seq_len;
+      a.c_prev = (t == 0) ? nullptr : c_all + t * RH;
+      a.h_prev = (t == 0) ? nullptr : hb + t * RH;
+      a.c_out = c_all + (t + 1) * RH;
+      a.h_out = hb + (t + 1) * RH;
+      a.gates = gb ? gb + t * RH * 4 : nullptr;
+      rc = ksplit == 8 ? launch_cluster_step<8>(ta1, ta2, tbw, a, stream)
+         : ksplit == 4 ? launch_cluster_step<4>(ta1, ta2, tbw, a, stream)
+                       : launch_cluster_step<2>(ta1, ta2, tbw, a, stream);
+      if (rc) return rc;
+    }
+    return EVC_OK;
+  }
   if ((rows <= 1024 || x2) && workspace != nullptr) {
     // Small-row steps (RNN_L2, student): one 128x256 tile per CTA would serialise the whole K on a few
     // SMs.  Split K over the SMs into f32 partial slabs, then one full-occupancy cell kernel sums

@@ -45,7 +45,8 @@ long long evc_launch_count(void);
 /* profiling experiments and tests only (bit flags): 128 = plain GEMMs store through the LSU path instead of TMA bulk
  * stores, 256 = no programmatic dependent launch for the GEMM kernels, 1024 = release the dependent grid at
  * kernel start instead of at the last tile, 2048 / 4096 = evc_lstm_seq_bwd always takes the slab path / the fused
- * dgrad + cell-backward kernel.  Also settable with the EVC_DEBUG environment variable. */
+ * dgrad + cell-backward kernel, 16384 = small-row forward steps run as the cluster split-K kernel of csrc/evc_cluster.cuh
+ * (measured slower than the slab path, off by default), 8192 = never.  Also settable with the EVC_DEBUG environment variable. */
 int evc_debug_set(int flags);
 
 /* ---- input: tf.nn.l2_normalize (train.py:256) + uniform gather (train.py:265-272) or
@@ -118,9 +119,11 @@ int evc_lstm_seq_fwd_steps(const void* x, long long x_step_stride, int Kx, const
                            int rows, int H, int T, int t_begin, int t_end, const int* seq_len, void* h_all,
                            float* c_all, void* gates_all, void* workspace, long long workspace_bytes,
                            const void* x_lo, const void* W_lo, void* h_lo_all, void* gates_lo_all, void* stream);
-/* Scratch needed by evc_lstm_seq_fwd / evc_lstm_seq_bwd for one cell (split-K partial slabs).  With a
- * workspace, steps with <= 1024 rows (RNN_L2, the student) run as a split-K GEMM over all SMs + a
- * full-occupancy cell kernel; without one (NULL) every step uses the fused-epilogue kernel. */
+/* Scratch needed by evc_lstm_seq_fwd / evc_lstm_seq_bwd for one cell (split-K partial slabs).
+ * Forward steps with <= 1024 rows (RNN_L2, the student): with a workspace a split-K GEMM into f32 slabs + a
+ * full-occupancy cell kernel; without one the fused-epilogue kernel.  (An alternative -- ONE kernel per step that splits
+ * K over a thread-block cluster and exchanges the partial sums through distributed shared memory, csrc/evc_cluster.cuh --
+ * is kept behind EVC_CLUSTER_STEP=1: parity-tested, measured 7 % slower.) */
 long long evc_lstm_workspace_bytes(int rows, int H, int Kx, int precise);
 
 /* The same layer with the recurrence as ONE persistent launch whose CTAs keep their slice of the recurrent

@@ -3,7 +3,7 @@ cell kernel (CUDA events, 20 repetitions after 3 warm-ups)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from efficientvideoclassification_youtube8m_b200 import ops
+from efficientvideoclassification_youtube8m_b200 import _lib, ops
 
 def bench(fn, n=20, w=3):
     for _ in range(w): fn()
@@ -15,7 +15,8 @@ def bench(fn, n=20, w=3):
     return e0.elapsed_time(e1) / n * 1e3
 
 reps = int(os.environ.get("REPS", "20"))
-for rows, Kx, H, T in [(256, 4096, 1024, 20), (256, 1024, 1024, 20), (256, 4096, 1024, 5), (1280, 1152, 1024, 6), (1280, 1024, 1024, 6), (1024, 4096, 1024, 5)]:
+for rows, Kx, H, T in [(256, 4096, 1024, 20), (256, 1024, 1024, 20), (256, 4096, 1024, 5), (256, 1024, 1024, 5),
+                       (512, 4096, 1024, 5), (1280, 1152, 1024, 6), (1024, 4096, 1024, 5)]:
     dev = "cuda"
     x = (torch.randn(T, rows, Kx, device=dev) * 0.5).to(torch.bfloat16)
     W = (torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)).to(torch.bfloat16)
@@ -31,6 +32,10 @@ for rows, Kx, H, T in [(256, 4096, 1024, 20), (256, 1024, 1024, 20), (256, 4096,
     zx = torch.empty(T * rows, 4 * H, device=dev)
     t_res = bench(lambda: ops.lstm_seq_fwd_resident(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, ws_rec), reps)
     t_step = bench(lambda: ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, ws), reps)
+    _lib.lib.evc_debug_set(8192)     # slab path: split-K GEMM + cell kernel
+    t_slab = bench(lambda: ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, ws), reps)
+    _lib.lib.evc_debug_set(0)
     t_zx = bench(lambda: ops.gemm(x.view(T * rows, Kx), W, T * rows, 4 * H, Kx, zx, b_mn=True, ldb=4 * H, bias=b), reps)
     print(f"rows {rows} Kx {Kx} H {H} T {T}: resident {t_res:8.1f} us (of which Zx GEMM {t_zx:7.1f}) -> {(t_res - t_zx) / T:6.1f} us/step rec;"
-          f"  per-step path {t_step:8.1f} us = {t_step / T:6.1f} us/step")
+          f"  per-step default (cluster split-K when eligible) {t_step:8.1f} us = {t_step / T:6.1f} us/step;"
+          f"  slab path {t_slab:8.1f} us = {t_slab / T:6.1f} us/step")

@@ -276,3 +276,53 @@ def test_lstm_seq_precise_mode_fwd_bwd():
     assert rel(dW, gW) < 3e-4, rel(dW, gW)
     assert rel(dX.view(T, rows, Kx), gx) < 3e-4, rel(dX.view(T, rows, Kx), gx)
     assert rel(db, gb) < 3e-4, rel(db, gb)
+
+
+@pytest.mark.parametrize("rows,Kx,H,T,want_ks", [(100, 1024, 128, 4, 8), (256, 4096, 1024, 3, 4), (256, 1024, 1024, 3, 4),
+                                                 (512, 1152, 1024, 2, 2), (130, 512, 256, 3, 4), (16, 512, 128, 5, 4)])
+def test_lstm_cluster_step_matches_slab_path(rows, Kx, H, T, want_ks):
+    """Small-row forward steps as one cluster split-K kernel each (partial sums through DSMEM, fused cell update;
+    csrc/evc_cluster.cuh) against the f64 reference and the slab path (split-K GEMM + cell kernel): cluster sizes 8, 4
+    and 2, the RNN_L2 shapes (256 rows, Kx = 4H and H), ragged row counts, zero / partial lengths, saved gates."""
+    from efficientvideoclassification_youtube8m_b200 import _lib, ops
+    torch.manual_seed(2)
+    dev = "cuda"
+    tiles = -(-rows // 128) * (H // 64)
+    ks = 8
+    while ks >= 2 and tiles * ks > 148:
+        ks //= 2
+    while ks >= 2 and Kx // 64 < 2 * ks:
+        ks //= 2
+    assert ks == want_ks                                  # (documents which cluster size the shape exercises)
+    ws = torch.empty(ops.lstm_workspace_bytes(rows, H, Kx), dtype=torch.uint8, device=dev)
+    x = (torch.randn(T, rows, Kx, device=dev) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(Kx + H, 4 * H, device=dev) * (2.0 / (Kx + H) ** 0.5)).to(torch.bfloat16)
+    b = torch.randn(4 * H, device=dev) * 0.1
+    seq_len = torch.randint(0, T + 1, (rows,), device=dev, dtype=torch.int32)
+    seq_len[:4] = torch.tensor([0, 1, T, T - 1], dtype=torch.int32)
+
+    def run(debug):
+        _lib.lib.evc_debug_set(debug)
+        try:
+            h_all = torch.zeros(T + 1, rows, H, dtype=torch.bfloat16, device=dev)
+            c_all = torch.zeros(T + 1, rows, H, device=dev)
+            gates = torch.zeros(T, rows, 4 * H, dtype=torch.bfloat16, device=dev)
+            n0 = _lib.launch_count()
+            ops.lstm_seq_fwd(x, rows * Kx, Kx, W, b, rows, H, T, seq_len, h_all, c_all, gates, ws)
+            torch.cuda.synchronize()
+            return h_all, c_all, gates, _lib.launch_count() - n0
+        finally:
+            _lib.lib.evc_debug_set(0)
+
+    h1, c1, g1, n1 = run(16384)          # cluster kernel (off by default: measured slower): one launch per step
+    h2, c2, g2, n2 = run(8192)           # slab path: GEMM + cell kernel per step
+    assert n1 == T and n2 == 2 * T
+    c_ref, h_ref, _ = _lstm_ref(x.double(), W.double(), b.double(), seq_len, T, H)
+    assert (c1[T].double() - c_ref).abs().max().item() < 2e-2
+    assert (h1[T].double() - h_ref).abs().max().item() < 2e-2
+    live = (torch.arange(T, device=dev).view(T, 1) < seq_len.view(1, rows)).unsqueeze(2)
+    assert (c1 - c2).abs().max().item() < 2e-3 and (h1.float() - h2.float()).abs().max().item() < 2e-2
+    assert ((g1.float() - g2.float()) * live).abs().max().item() < 2e-2
+    assert torch.all(h1[:, 0] == 0) and torch.all(c1[:, 0] == 0)        # the zero-length row keeps the zero state
+    h3, c3, g3, _ = run(16384)
+    assert torch.equal(h1, h3) and torch.equal(c1, c3) and torch.equal(g1, g3)     # deterministic
