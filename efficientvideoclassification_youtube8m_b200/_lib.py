@@ -28,6 +28,7 @@ SIGNATURES = {
     "evc_random_uniform": [C.c_ulonglong, C.c_ulonglong, P, L, P],
     "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
     "evc_gemm_bf16x2": [P, P, I, L, P, P, I, L, I, I, I, P, I, L, P, I, I, P],
+    "evc_gemm_bf16_sumsq": [P, P, I, L, P, P, I, L, I, I, I, P, L, P, P],
     "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
     "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P, P, P, P, P],
     "evc_lstm_workspace_bytes": [I, I, I, I],
@@ -47,6 +48,8 @@ SIGNATURES = {
     "evc_colsum_bf16": [P, L, I, L, P, P],
     "evc_sumsq": [P, P, F, L, P, P, P],
     "evc_clip_adam": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P, P],
+    "evc_clip_adam_fused": [P, P, P, P, L, P, F, F, P, F, F, F, P, I, L, P, P, P, P, P, P],
+    "evc_reg_cross": [P, L, P, P, L, P, I, I, P, P],
     "evc_batch_metrics": [P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "evc_topk": [P, I, I, I, P, P, P, P, P],
 }

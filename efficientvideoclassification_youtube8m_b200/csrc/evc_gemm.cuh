@@ -67,6 +67,9 @@ struct GemmArgs {
   int tma_store;       // 1: C is written with TMA bulk stores through tensor map tmC (row offset ks*split_rows)
   int split_rows;      // rows between partial slabs in tmC's row coordinate
   const float* bias;   // [N] or null
+  float* sumsq_out;    // null, or: *sumsq_out += sum of the squares of the f32 C this launch stores (plain stores only) --
+                       // the per-variable gradient norm of slim's clip_gradient_norms, taken where the weight
+                       // gradient is produced instead of by a second pass over it
   // ---- EPI_LSTM_FWD / BWD (row r, hidden unit u; H = N/4 for fwd, N for bwd)
   int H;
   int t;                        // time step, row is live iff t < seq_len[r]
@@ -428,6 +431,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           constexpr int CW = 32;                      // f32 columns per box (bf16: 64 columns, same 128 B)
           const int cols_per_box = args.c_bf16 ? 2 * CW : CW;
           int buf = 0;
+          float ssq = 0.f;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += cols_per_box) {
             const int col0 = n_blk * BN + c0;
@@ -459,6 +463,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                 for (int j = 0; j < 32; ++j)
                   if (col0 + j < args.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(args.bias + col0 + j));
               }
+              if (args.sumsq_out != nullptr && row_ok) {
+                // (columns past N hold exact zeros: TMA zero-fills the out-of-bounds part of the B tile)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ssq = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), ssq);
+              }
             }
             if (col0 >= args.N || nrows <= 0) continue;   // warp-uniform: nothing to store
             // the box that used this buffer two iterations ago must have been read by the TMA engine
@@ -482,6 +491,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           }
           if (lane == 0) tma_store_wait_read<0>();              // staging is free again for the next tile
           __syncwarp();
+          if (args.sumsq_out != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+            if (lane == 0 && ssq != 0.f) atomicAdd(args.sumsq_out, ssq);
+          }
         } else
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -528,10 +542,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               for (int i = 0; i < 4; ++i) {
                 const int rr = pr + 8 * i;
                 if (rr < nrows) {
+                  float* dst = cp + static_cast<long long>(rr) * args.ldc + pc;
+                  if (vec) {            // one 16-byte reduction (RED.E.ADD.F32x4) instead of four scalar ones
+                    atomicAdd(reinterpret_cast<float4*>(dst),
+                              make_float4(st_f[rr * 17 + pc], st_f[rr * 17 + pc + 1], st_f[rr * 17 + pc + 2],
+                                          st_f[rr * 17 + pc + 3]));
+                  } else {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (col0 + pc + k < args.N)
-                      atomicAdd(cp + static_cast<long long>(rr) * args.ldc + pc + k, st_f[rr * 17 + pc + k]);
+                    for (int k = 0; k < 4; ++k)
+                      if (col0 + pc + k < args.N) atomicAdd(dst + k, st_f[rr * 17 + pc + k]);
+                  }
                 }
               }
               __syncwarp();

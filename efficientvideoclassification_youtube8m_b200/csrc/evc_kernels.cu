@@ -381,10 +381,10 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
                      const int* __restrict__ seq_len, int t, int rows, int H,
                      __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dc_out,
                      float* __restrict__ dh_pass_out, float* __restrict__ dbias,
-                     const __nv_bfloat16* __restrict__ gates_lo, __nv_bfloat16* __restrict__ dz_lo) {
+                     const __nv_bfloat16* __restrict__ gates_lo, __nv_bfloat16* __restrict__ dz_lo, int red_vec) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL (see evc_ptx.cuh)
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  __shared__ float red[8][4][132];               // [row lane][gate][128 units + pad]
+  __shared__ __align__(16) float red[8][4][132];               // [row lane][gate][128 units + pad]
   const int ql = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int u = (blockIdx.x * 32 + ql) * 4;      // first of this thread's 4 units
   const int r = blockIdx.y * 8 + rl;
@@ -468,12 +468,22 @@ lstm_cell_bwd_kernel(const float* __restrict__ dh_part, int S, long long part_st
     for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(&red[rl][g][ql * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 512; i += 256) {
-    const int g = i >> 7, c = i & 127;
-    float acc = 0.f;
+  if (threadIdx.x < 128) {           // 4 gates x 32 quads: one 16-byte vector reduction per thread (red.global.v4.f32)
+    const int g = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r8 = 0; r8 < 8; ++r8) acc += red[r8][g][c];
-    if (acc != 0.f) atomicAdd(dbias + g * H + blockIdx.x * 128 + c, acc);
+    for (int r8 = 0; r8 < 8; ++r8) {
+      const float4 a = *reinterpret_cast<const float4*>(&red[r8][g][c]);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    float* dst = dbias + g * H + blockIdx.x * 128 + c;
+    if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f) {
+      if (red_vec && (reinterpret_cast<uintptr_t>(dbias) & 15) == 0) {
+        atomicAdd(reinterpret_cast<float4*>(dst), acc);      // sm_90+: one 16-byte RED
+      } else {
+        atomicAdd(dst + 0, acc.x); atomicAdd(dst + 1, acc.y); atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
+      }
+    }
   }
 }
 
@@ -735,19 +745,30 @@ __global__ void sumsq_kernel(const float* __restrict__ g, const float* __restric
 // [TF clip_ops.clip_by_norm] g * c * min(rsqrt(sum g^2), 1/c), then [TF ApplyAdam]
 //   m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= lr_t * m / (sqrt(v) + eps)
 // and refresh of the bf16 operand copy of w (row pitch ld_shadow, `cols` columns per row).
+// The squared norm of the regularised gradient g + wd*w is  *normsq  (a sumsq pass)  +  the parts taken where they
+// were cheap (all nullable):  *normsq_fused = sum g^2 from the weight-gradient GEMM's epilogue,  *reg_cross = <g, w>
+// (evc_reg_cross)  and  *reg_wsq = sum w^2:   |g + wd w|^2 = |g|^2 + 2 wd <g,w> + wd^2 |w|^2.
+// wsq_out (nullable): += sum of the squares of the UPDATED weights (next step's reg_wsq / regulariser value).
 __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n, const float* __restrict__ normsq, float clip,
                                  float wd, const float* __restrict__ lr_t, float b1, float b2, float eps,
                                  __nv_bfloat16* __restrict__ shadow, int cols, long long ld_shadow,
-                                 __nv_bfloat16* __restrict__ shadow_lo) {
+                                 __nv_bfloat16* __restrict__ shadow_lo, const float* __restrict__ normsq_fused,
+                                 const float* __restrict__ reg_cross, const float* __restrict__ reg_wsq,
+                                 float* __restrict__ wsq_out) {
   PDL_PROLOGUE();
+  __shared__ float sh[32];
   float scale = 1.f;
   if (clip > 0.f) {
-    const float ns = *normsq;
+    float ns = *normsq;
+    if (normsq_fused != nullptr) ns += *normsq_fused;
+    if (reg_cross != nullptr) ns += 2.f * wd * *reg_cross;
+    if (reg_wsq != nullptr) ns += wd * wd * *reg_wsq;
     scale = (ns > 0.f) ? clip * fminf(rsqrtf(ns), 1.0f / clip) : 1.f;
   }
   const float lr = *lr_t;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
+  float wacc = 0.f;
   // 4 parameters per thread and iteration (every tensor size and `cols` is a multiple of 4)
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -765,12 +786,57 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
       ma[k] += (gi - ma[k]) * c1;
       va[k] += (gi * gi - va[k]) * c2;
       wa[k] -= lr * ma[k] / (sqrtf(va[k]) + eps);
+      wacc = fmaf(wa[k], wa[k], wacc);
     }
     *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
     *reinterpret_cast<float4*>(w + i) = make_float4(wa[0], wa[1], wa[2], wa[3]);
     if (shadow) store4_split(shadow, shadow_lo, (i / cols) * ld_shadow + (i % cols), wa);
   }
+  if (wsq_out != nullptr) {
+    wacc = block_sum(wacc, sh);
+    if (threadIdx.x == 0) atomicAdd(wsq_out, wacc);
+  }
+}
+
+// <g, w> of a fully connected layer without touching g or w:  g = X^T dL (the weight-gradient GEMM) and
+// logits = X w + bias, hence  <g, w> = <X^T dL, w> = <dL, X w> = sum_b sum_n dL[b,n] * (logits[b,n] - bias[n]).
+// dL: bf16 gradient w.r.t. the logits as the weight-gradient GEMM reads it (+ residual plane in split-bf16 mode).
+// out[0] += the sum.  One block per row.
+__global__ void reg_cross_kernel(const float* __restrict__ logits, long long ld_logits,
+                                 const __nv_bfloat16* __restrict__ dl, const __nv_bfloat16* __restrict__ dl_lo,
+                                 long long ld_dl, const float* __restrict__ bias, int N, int vec,
+                                 float* __restrict__ out) {
+  PDL_PROLOGUE();
+  __shared__ float sh[32];
+  const float* lrow = logits + static_cast<long long>(blockIdx.x) * ld_logits;
+  const __nv_bfloat16* drow = dl + static_cast<long long>(blockIdx.x) * ld_dl;
+  const __nv_bfloat16* drow_lo = dl_lo ? dl_lo + static_cast<long long>(blockIdx.x) * ld_dl : nullptr;
+  float acc = 0.f;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x, nt = gridDim.y * blockDim.x;
+  int n0 = 0;
+  if (vec) {                       // 4 columns per thread and iteration: 16-byte logits, 8-byte gradient loads
+    const int n4 = N >> 2;
+    for (int q = t; q < n4; q += nt) {
+      const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * q);
+      float d[4];
+      load4_split(drow, drow_lo, 4 * q, d);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias + 4 * q));
+      acc = fmaf(d[0], l.x - b.x, acc);
+      acc = fmaf(d[1], l.y - b.y, acc);
+      acc = fmaf(d[2], l.z - b.z, acc);
+      acc = fmaf(d[3], l.w - b.w, acc);
+    }
+    n0 = n4 << 2;
+  }
+  for (int n = n0 + t; n < N; n += nt) {
+    float d = __bfloat162float(drow[n]);
+    if (drow_lo != nullptr) d += __bfloat162float(drow_lo[n]);
+    acc = fmaf(d, lrow[n] - (bias != nullptr ? __ldg(bias + n) : 0.f), acc);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(out, acc);
 }
 
 // eval_util.py:118-124 top_k_triplets: the k largest predictions of a video.  Exact; the
@@ -970,6 +1036,11 @@ int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, con
   const int col_blocks = H / 128;
   const int row_groups = (rows + 7) / 8;
   if (row_groups > 65535) return set_error(EVC_ERR_UNSUPPORTED, "lstm_cell_bwd: more than 524280 rows");
+  static int red_vec = -1;   // EVC_BIAS_RED=1: scalar float atomics for the bias sums (A/B experiment; default 16-byte REDs)
+  if (red_vec < 0) {
+    const char* e = getenv("EVC_BIAS_RED");
+    red_vec = (e && atoi(e) == 1) ? 0 : 1;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(col_blocks), static_cast<unsigned>(row_groups));
   cfg.blockDim = dim3(256);
@@ -982,7 +1053,7 @@ int launch_lstm_cell_bwd(const float* dh_part, int S, long long part_stride, con
   cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, dh_part, S, part_stride, static_cast<const __nv_bfloat16*>(gates),
                      c_prev, dh_ext, ld_dh_ext, dh_pass_in, ld_dh_pass_in, dc_in, ld_dc_in, seq_len, t, rows, H,
                      static_cast<__nv_bfloat16*>(dz_out), dc_out, dh_pass_out, dbias,
-                     static_cast<const __nv_bfloat16*>(gates_lo), static_cast<__nv_bfloat16*>(dz_lo));
+                     static_cast<const __nv_bfloat16*>(gates_lo), static_cast<__nv_bfloat16*>(dz_lo), red_vec);
   count_launch();
   return check_launch("lstm_cell_bwd");
 }
@@ -1186,21 +1257,54 @@ extern "C" int evc_sumsq(const float* g, const float* w, float weight_decay, lon
   return check_launch("sumsq");
 }
 
-extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
-                             float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2,
-                             float eps, void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo,
-                             void* stream) {
+static int clip_adam_impl(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
+                          float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2, float eps,
+                          void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo, const float* normsq_fused,
+                          const float* reg_cross, const float* reg_wsq, float* wsq_out, void* stream) {
   if (shadow_bf16 && cols <= 0) return set_error(EVC_ERR_ARG, "clip_adam: cols required with a bf16 copy");
   if (n % 4 != 0 || (shadow_bf16 && (cols % 4 != 0 || ld_shadow % 4 != 0)) ||
       ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
         reinterpret_cast<uintptr_t>(v)) & 15))
     return set_error(EVC_ERR_ARG, "clip_adam: tensors must be 16-byte aligned with sizes/cols multiple of 4");
+  if (normsq == nullptr && clip_norm > 0.f) return set_error(EVC_ERR_ARG, "clip_adam: normsq required when clipping");
   pdl_launch(clip_adam_kernel, dim3(grid_for(n / 4, 256, 148 * 8)), dim3(256), 0, EVC_STREAM(stream), 
       w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps,
       static_cast<__nv_bfloat16*>(shadow_bf16), cols > 0 ? cols : 1, ld_shadow,
-      static_cast<__nv_bfloat16*>(shadow_lo));
+      static_cast<__nv_bfloat16*>(shadow_lo), normsq_fused, reg_cross, reg_wsq, wsq_out);
   count_launch();
   return check_launch("clip_adam");
+}
+
+extern "C" int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
+                             float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2,
+                             float eps, void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo,
+                             void* stream) {
+  return clip_adam_impl(w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps, shadow_bf16, cols,
+                        ld_shadow, shadow_lo, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int evc_clip_adam_fused(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
+                                   float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2,
+                                   float eps, void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo,
+                                   const float* normsq_fused, const float* reg_cross, const float* reg_wsq,
+                                   float* wsq_out, void* stream) {
+  return clip_adam_impl(w, g, m, v, n, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps, shadow_bf16, cols,
+                        ld_shadow, shadow_lo, normsq_fused, reg_cross, reg_wsq, wsq_out, stream);
+}
+
+extern "C" int evc_reg_cross(const float* logits, long long ld_logits, const void* dlogits, const void* dlogits_lo,
+                             long long ld_dlogits, const float* bias, int B, int N, float* out, void* stream) {
+  if (B <= 0 || N <= 0) return set_error(EVC_ERR_ARG, "reg_cross: empty problem");
+  // vector path: every row of the three operands starts on a 16- (f32) / 8-byte (bf16) boundary
+  const int vec = ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(dlogits) | reinterpret_cast<uintptr_t>(dlogits_lo)) & 7) == 0 &&
+                  ld_logits % 4 == 0 && ld_dlogits % 4 == 0;
+  const int chunks = N >= 8192 ? 4 : (N >= 2048 ? 2 : 1);
+  pdl_launch(reg_cross_kernel, dim3(B, chunks), dim3(256), 0, EVC_STREAM(stream), logits, ld_logits,
+             static_cast<const __nv_bfloat16*>(dlogits), static_cast<const __nv_bfloat16*>(dlogits_lo), ld_dlogits, bias,
+             N, vec, out);
+  count_launch();
+  return check_launch("reg_cross");
 }
 
 extern "C" int evc_batch_metrics(const float* P, const unsigned char* labels, int B, int V, int k, const int* idx,

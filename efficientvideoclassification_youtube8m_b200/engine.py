@@ -83,6 +83,7 @@ class HLstmEngine:
         self.training = training
         self.precise = bool(getattr(params, "precise", False))
         self.overlap = overlap_mode()
+        self._fused_norms = False    # inside lstm_backward: weight-gradient GEMMs also leave |dW|^2 (params.norm_aux)
         self._side: Optional[torch.cuda.Stream] = None
         self._events = []
         dev = params.device
@@ -299,6 +300,14 @@ class HLstmEngine:
         dz_lo = layer.dz_lo.view(R, 4 * H) if self.precise else None
         h_lo = layer.h_lo.view(-1, H) if self.precise else None
         gW = p.g[p.kernel(level, cell)]
+        if self._fused_norms:
+            # |dW|^2 accumulated by the two GEMMs' epilogues (the clip of slim's train op is per variable)
+            ss = p.norm_aux[(level * 2 + cell) * 2, 0:1]
+            ops.gemm_sumsq(x2d, dz, Kx, 4 * H, R, gW[:Kx], ss, a_mn=True, b_mn=True, lda=Kx, ldc=4 * H,
+                           A_lo=x2d_lo, B_lo=dz_lo)
+            ops.gemm_sumsq(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], ss, a_mn=True, b_mn=True, lda=H,
+                           ldc=4 * H, A_lo=h_lo, B_lo=dz_lo)
+            return
         ops.gemm(x2d, dz, Kx, 4 * H, R, gW[:Kx], a_mn=True, b_mn=True, lda=Kx, ldc=4 * H, A_lo=x2d_lo, B_lo=dz_lo)
         ops.gemm(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], a_mn=True, b_mn=True, lda=H, ldc=4 * H,
                  A_lo=h_lo, B_lo=dz_lo)
@@ -334,10 +343,24 @@ class HLstmEngine:
                  A_lo=self.dG_lo, B_lo=lo(p.gates_w))
         ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=8, accumulate=True,
                  A_lo=self.dE_lo, B_lo=lo(p.experts_w))
-        ops.gemm(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], a_mn=True, b_mn=True,
-                 A_lo=self.state_lo, B_lo=self.dG_lo)
-        ops.gemm(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], a_mn=True, b_mn=True,
-                 A_lo=self.state_lo, B_lo=self.dE_lo)
+        if p.fused_norms():
+            # the two matrices' |g|^2 from the GEMM epilogues and <g, w> from the logits (the regulariser's
+            # gradient wd*w enters the clipped norm, train.py:324-334): no sumsq pass over g and w in the optimizer
+            p.begin_fused_norms(8, 11)
+            ops.gemm_sumsq(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], p.norm_aux[8, 0:1], a_mn=True,
+                           b_mn=True, A_lo=self.state_lo, B_lo=self.dG_lo)
+            ops.gemm_sumsq(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], p.norm_aux[9, 0:1], a_mn=True,
+                           b_mn=True, A_lo=self.state_lo, B_lo=self.dE_lo)
+            ops.reg_cross(self.G, self.G.stride(0), self.dG, self.lddg, None, B, self.ldg, p.norm_aux[8, 1:2],
+                          self.dG_lo)
+            ops.reg_cross(self.E, self.E.stride(0), self.dE, self.ldde, p.w[p.experts_b], B, self.lde,
+                          p.norm_aux[9, 1:2], self.dE_lo)
+            p.end_fused_norms((8, 9))
+        else:
+            ops.gemm(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], a_mn=True, b_mn=True,
+                     A_lo=self.state_lo, B_lo=self.dG_lo)
+            ops.gemm(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], a_mn=True, b_mn=True,
+                     A_lo=self.state_lo, B_lo=self.dE_lo)
         gbe = p.g[p.experts_b]
         ops.fill_f32(gbe, 0.0)
         ops.colsum_bf16(self.dE, B, self.lde, self.ldde, gbe)
@@ -352,6 +375,9 @@ class HLstmEngine:
         # ---- RNN_L2 (cell 1 first: its input gradient feeds cell 0)
         a2, b2 = self.l2
         a, b = self.l1
+        self._fused_norms = p.fused_norms()
+        if self._fused_norms:
+            p.begin_fused_norms(0, 8)
         if self.overlap & OVERLAP_WGRAD:
             # dz of a cell is final once its recurrence is done: its weight-gradient GEMMs (tensor-bound, no
             # dependants until the optimizer) run on the side stream next to the latency-bound recurrence
@@ -385,3 +411,6 @@ class HLstmEngine:
         self._cell_wgrad(a, 0, 0, self.x.view(-1, D), D, self.x_lo.view(-1, D) if px else None)
         if side is not None:
             main.wait_stream(side)
+        if self._fused_norms:
+            p.end_fused_norms((0, 2, 4, 6))
+            self._fused_norms = False

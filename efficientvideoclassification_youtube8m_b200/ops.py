@@ -48,6 +48,25 @@ def gemm(A, B, M, N, K, out, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=Non
     return out
 
 
+def gemm_sumsq(A, B, M, N, K, out, sumsq_out, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, A_lo=None,
+               B_lo=None):
+    """Weight-gradient GEMM: out[M,N] (f32) = A @ B and sumsq_out[0] += sum(out^2) from the epilogue."""
+    lda = lda if lda is not None else A.stride(0)
+    ldb = ldb if ldb is not None else B.stride(0)
+    ldc = ldc if ldc is not None else out.stride(0)
+    assert out.dtype == torch.float32 and sumsq_out.dtype == torch.float32
+    check(lib.evc_gemm_bf16_sumsq(ptr(A), ptr(A_lo), int(a_mn), lda, ptr(B), ptr(B_lo), int(b_mn), ldb, M, N, K,
+                                  ptr(out), ldc, ptr(sumsq_out), stream()), "evc_gemm_bf16_sumsq")
+    return out
+
+
+def reg_cross(logits, ld_logits, dlogits, ld_dlogits, bias, B, N, out, dlogits_lo=None):
+    """out[0] += <g, w> of a fully connected layer = sum dlogits * (logits - bias)."""
+    _cuda(logits, dlogits, bias, out, dlogits_lo)
+    check(lib.evc_reg_cross(ptr(logits), ld_logits, ptr(dlogits), ptr(dlogits_lo), ld_dlogits, ptr(bias), B, N,
+                            ptr(out), stream()), "evc_reg_cross")
+
+
 def frames_pack(src, frame_idx, K, num_chunks, normalize, out_bf16=None, out_f32=None, out_lo=None):
     _cuda(src, frame_idx, out_bf16, out_f32, out_lo)
     B, T, D = src.shape
@@ -217,7 +236,14 @@ def sumsq(g, w, weight_decay, out, out_wsq=None):
 
 
 def clip_adam(w, g, m, v, normsq, clip_norm, weight_decay, lr_t, beta1, beta2, eps, shadow=None, cols=0,
-              ld_shadow=0, shadow_lo=None):
+              ld_shadow=0, shadow_lo=None, normsq_fused=None, reg_cross=None, reg_wsq=None, wsq_out=None):
+    """normsq_fused / reg_cross / reg_wsq / wsq_out: the norm assembled from its parts (evc_clip_adam_fused)."""
+    if normsq_fused is not None or reg_cross is not None or reg_wsq is not None or wsq_out is not None:
+        check(lib.evc_clip_adam_fused(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(normsq), clip_norm, weight_decay,
+                                      ptr(lr_t), beta1, beta2, eps, ptr(shadow), cols, ld_shadow, ptr(shadow_lo),
+                                      ptr(normsq_fused), ptr(reg_cross), ptr(reg_wsq), ptr(wsq_out), stream()),
+              "evc_clip_adam_fused")
+        return
     check(lib.evc_clip_adam(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(normsq), clip_norm, weight_decay,
                             ptr(lr_t), beta1, beta2, eps, ptr(shadow), cols, ld_shadow, ptr(shadow_lo), stream()),
           "evc_clip_adam")

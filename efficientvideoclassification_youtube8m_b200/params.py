@@ -11,6 +11,7 @@ train_convert_model.py:501-511) held in HBM:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -97,6 +98,14 @@ class HLstmParams:
                     self.shadow_lo[n] = torch.zeros(shp[0], ld, dtype=torch.bfloat16, device=self.device)
         self.normsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
         self.wsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
+        # Norms taken where the gradients are produced (one process, CUDA): the weight-gradient GEMMs leave sum g^2 of
+        # their matrix in norm_aux[i, 0] (evc_gemm_bf16_sumsq), evc_reg_cross leaves <g, w> of the two regularised
+        # matrices in norm_aux[i, 1], and the clip+Adam kernel accumulates sum w^2 of the weights it writes into
+        # wsq_next -- so the optimizer needs no sumsq pass over the matrices (`begin_fused_norms`, `apply_gradients`).
+        self.norm_aux = torch.zeros(len(self.names), 2, dtype=torch.float32, device=self.device)
+        self.wsq_next = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
+        self._fused_ready = set()     # variables whose norm_aux row is fresh from the latest backward
+        self._wsq_valid = False       # wsq_next holds sum w^2 of the CURRENT weights of the regularised matrices
         self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
         # autograd handle: the kernels write weight gradients straight into flat_g, the token only makes
@@ -195,7 +204,26 @@ class HLstmParams:
                 sd[name] = z[k]
         self.load_state_dict({n: sd[n] for n in self.names if n in sd}, strict=True)
 
+    # ---- gradient norms from the producers (see __init__)
+    def fused_norms(self) -> bool:
+        """Whether the engine should take the matrices' gradient norms in the weight-gradient GEMM epilogues: one
+        process only (with data parallelism the norm is that of the AVERAGED gradient), EVC_FUSED_NORMS=0 disables."""
+        if self.device.type != "cuda" or os.environ.get("EVC_FUSED_NORMS", "1") == "0":
+            return False
+        import torch.distributed as dist
+        return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+
+    def begin_fused_norms(self, first: int, last: int) -> None:
+        """Before the weight-gradient GEMMs of names[first:last]: zero their partial-norm slots."""
+        ops.fill_f32(self.norm_aux[first:last], 0.0)
+        self._fused_ready -= set(range(first, last))
+
+    def end_fused_norms(self, indices) -> None:
+        """After them: the slots of `indices` are complete once the launches issued so far have run."""
+        self._fused_ready |= set(indices)
+
     def refresh_shadows(self) -> None:
+        self._wsq_valid = False           # (called whenever the masters were changed from outside)
         for n, s in self.shadow.items():
             rows, cols = self.shapes[n]
             ops.cast_bf16(self.w[n], s, rows, cols, self.ld[n], self.shadow_lo.get(n))
@@ -274,6 +302,8 @@ class HLstmParams:
                 ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],
                               float(clip_gradient_norm), 0.0, self.lr_t, beta1, beta2, eps, None, 0, 0)
         self._master_stale = world > 1
+        self._wsq_valid = False
+        self._fused_ready -= set(range(first, last))
         return handles
 
     def sync_master_weights(self, rank: int, world: int, group=None, include_slots: bool = False) -> None:
@@ -323,8 +353,26 @@ class HLstmParams:
         if advance:
             ops.adam_lr(self.adam_step, lr, beta1, beta2, self.lr_t)
         reg = (self.gates_w, self.experts_w)
+        fused = {i for i in range(first, last) if i in self._fused_ready and len(self.shapes[self.names[i]]) == 2}
+        self._fused_ready -= set(range(first, last))
+        reg_idx = [i for i in range(first, last) if self.names[i] in reg]
+        reg_fused = bool(reg_idx) and all(i in fused for i in reg_idx)
+        if reg_idx and not reg_fused:
+            fused -= set(reg_idx)
+            self._wsq_valid = False       # their clip+Adam launches below do not maintain wsq_next
+        if reg_fused:
+            # sum w^2 of the regularised matrices: left by the previous step's clip+Adam launches (or one pass over
+            # w after the weights were set from outside); it is this step's regulariser value and norm term
+            lo, hi = reg_idx[0], reg_idx[-1] + 1
+            if not self._wsq_valid:
+                ops.fill_f32(self.wsq_next[lo:hi], 0.0)
+                for i in reg_idx:
+                    ops.sumsq(self.w[self.names[i]], None, 0.0, self.wsq_next[i:i + 1], None)
+            self.wsq[lo:hi].copy_(self.wsq_next[lo:hi])
+            ops.fill_f32(self.wsq_next[lo:hi], 0.0)
+            self._wsq_valid = True
         for i, n in enumerate(self.names):
-            if not first <= i < last:
+            if not first <= i < last or i in fused:
                 continue
             w = self.w[n] if n in reg else None
             ops.sumsq(self.g[n], w, wd, self.normsq[i:i + 1], self.wsq[i:i + 1] if w is not None else None)
@@ -333,6 +381,12 @@ class HLstmParams:
                 continue
             shadow = self.shadow.get(n)
             cols = self.shapes[n][1] if shadow is not None else 0
+            extra = {}
+            if i in fused:
+                extra["normsq_fused"] = self.norm_aux[i, 0:1]
+                if n in reg:
+                    extra.update(reg_cross=self.norm_aux[i, 1:2], reg_wsq=self.wsq[i:i + 1],
+                                 wsq_out=self.wsq_next[i:i + 1])
             ops.clip_adam(self.w[n], self.g[n], self.m[n], self.v[n], self.normsq[i:i + 1],
                           float(clip_gradient_norm), wd if n in reg else 0.0, self.lr_t, beta1, beta2, eps,
-                          shadow, cols, self.ld.get(n, 0), self.shadow_lo.get(n))
+                          shadow, cols, self.ld.get(n, 0), self.shadow_lo.get(n), **extra)

@@ -101,6 +101,12 @@ int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
 int evc_gemm_bf16x2(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B, const void* B_lo,
                     int b_mn_major, long long ldb, int M, int N, int K, void* C, int c_is_bf16, long long ldc,
                     const float* bias, int split_k, int accumulate, void* stream);
+/* Weight-gradient form: C f32 = A * B stored plainly (no bias, no split-K; A_lo / B_lo nullable residual planes) and
+ * sumsq_out[0] += sum of C^2, taken in the epilogue from the accumulators -- the per-variable gradient norm of slim's
+ * clip_gradient_norms (train.py:329-334) without a second pass over the gradient.  C must be 16-byte aligned. */
+int evc_gemm_bf16_sumsq(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B, const void* B_lo,
+                        int b_mn_major, long long ldb, int M, int N, int K, float* C, long long ldc, float* sumsq_out,
+                        void* stream);
 
 /* ---- tf.nn.dynamic_rnn(BasicLSTMCell(H, forget_bias=1.0), x, sequence_length) for ONE cell of
  * the MultiRNNCell stack (frame_level_models.py:221-257, 291-328), all `rows` sequences at once.
@@ -205,6 +211,21 @@ int evc_adam_lr(long long* step, float lr, float beta1, float beta2, float* lr_t
 int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
                   float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2, float eps,
                   void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo, void* stream);
+/* The same update with the squared norm of the regularised gradient assembled from parts taken where they are cheap
+ * instead of by an evc_sumsq pass over g and w (slim clip_gradient_norms on g + wd*w, train.py:329-334):
+ *   |g + wd*w|^2 = *normsq + *normsq_fused + 2*wd * *reg_cross + wd^2 * *reg_wsq      (the last three nullable)
+ * normsq_fused = sum g^2 from the weight-gradient GEMM's epilogue (evc_gemm_bf16_sumsq), reg_cross = <g, w>
+ * (evc_reg_cross), reg_wsq = sum w^2.  wsq_out (nullable): += sum of the squares of the UPDATED weights, i.e. the
+ * next step's reg_wsq and regulariser value (video_level_models.py:428,434). */
+int evc_clip_adam_fused(float* w, const float* g, float* m, float* v, long long n, const float* normsq,
+                        float clip_norm, float weight_decay, const float* lr_t, float beta1, float beta2, float eps,
+                        void* shadow_bf16, int cols, long long ld_shadow, void* shadow_lo, const float* normsq_fused,
+                        const float* reg_cross, const float* reg_wsq, float* wsq_out, void* stream);
+/* <g, w> of a fully connected layer (slim.fully_connected, video_level_models.py:423-435) from its logits and the
+ * gradient w.r.t. them, without reading g or w:  g = X^T dL, logits = X w + bias  =>  <g, w> = sum dL * (logits - bias).
+ * logits f32 [B, ld_logits], dlogits bf16 [B, ld_dlogits] (+ residual plane, nullable), bias [N] nullable; out[0] += sum. */
+int evc_reg_cross(const float* logits, long long ld_logits, const void* dlogits, const void* dlogits_lo,
+                  long long ld_dlogits, const float* bias, int B, int N, float* out, void* stream);
 
 /* ---- eval_util.py:118-124 top_k_triplets: per video the k largest predictions (value desc,
  * lower class index first among equals), their values and (nullable) labels. */

@@ -1,0 +1,26 @@
+#!/bin/bash
+# 1-GPU A/B in one call (same box): bias-sum reductions of the cell backward (EVC_BIAS_RED=1 scalar atomics, default
+# 16-byte REDs) and the gradient norms from the producers (EVC_FUSED_NORMS=0: sumsq pass; default: GEMM epilogues)
+OUT=gpurun_out/r02_ab_norms_biasred.txt
+: > $OUT
+run() {
+  env "$@" python bench.py --steps 20 --warmup 3 --skip-cpu --skip-tfrecord --skip-configs --skip-f32-e2e --skip-infer \
+    > gpurun_out/_ab.json 2> gpurun_out/_ab.err
+  python - "$*" <<'PY' >> gpurun_out/r02_ab_norms_biasred.txt
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/_ab.json").read().strip().splitlines()[-1])
+    print(sys.argv[1], "| ms_per_step %.3f" % d["ms_per_step"], "videos/s %.0f" % d["value"],
+          "e2e ms %.3f" % d["e2e"]["ms_per_step"], "launches", d["gpu_launches"], "SM MHz", d["clocks"]["sm_mhz"],
+          "losses", {k: round(v, 4) for k, v in d["losses"].items() if k in ("teacher_loss", "student_loss")})
+except Exception as e:
+    print(sys.argv[1], "failed:", e, open("gpurun_out/_ab.err").read()[-1500:])
+PY
+}
+for rep in 1 2; do
+  run EVC_FUSED_NORMS=1 EVC_BIAS_RED=4
+  run EVC_FUSED_NORMS=0 EVC_BIAS_RED=4
+  run EVC_FUSED_NORMS=1 EVC_BIAS_RED=1
+  run EVC_FUSED_NORMS=0 EVC_BIAS_RED=1
+done
+cat $OUT

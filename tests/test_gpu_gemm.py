@@ -326,3 +326,87 @@ def test_lstm_cluster_step_matches_slab_path(rows, Kx, H, T, want_ks):
     assert torch.all(h1[:, 0] == 0) and torch.all(c1[:, 0] == 0)        # the zero-length row keeps the zero state
     h3, c3, g3, _ = run(16384)
     assert torch.equal(h1, h3) and torch.equal(c1, c3) and torch.equal(g1, g3)     # deterministic
+
+
+@pytest.mark.parametrize("M,N,K,precise", [(1152, 4096, 2560, False), (512, 1412, 256, False), (300, 712, 192, True)])
+def test_gemm_sumsq_epilogue(M, N, K, precise):
+    """Weight-gradient form (A and B MN-major): same C as the plain GEMM and sum(C^2) from the epilogue, accumulated
+    over two launches into one slot (the x and h parts of one LSTM kernel matrix)."""
+    from efficientvideoclassification_youtube8m_b200 import ops
+    Mp, Np = ops.pad8(M, 8), ops.pad8(N, 8)
+    A, B = _mk((K, Mp), 11), _mk((K, Np), 12)
+    A_lo = (_mk((K, Mp), 13) * 2.0 ** -9) if precise else None
+    B_lo = (_mk((K, Np), 14) * 2.0 ** -9) if precise else None
+    ref = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, M, N, K, ref, a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ss = torch.zeros(2, device="cuda")
+    ops.gemm_sumsq(A, B, M, N, K, out, ss[0:1], a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
+    ops.gemm_sumsq(A, B, M, N, K, out, ss[0:1], a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    want = 2.0 * ref.double().pow(2).sum().item()
+    assert abs(ss[0].item() - want) <= 2e-5 * want, (ss[0].item(), want)
+    assert ss[1].item() == 0.0
+    # rejected before any launch: bf16 C has no sumsq form, unaligned C
+    from efficientvideoclassification_youtube8m_b200._lib import EvcError
+    with pytest.raises(EvcError):
+        ops.gemm_sumsq(A, B, M, N, K, torch.empty(M * N + 1, device="cuda")[1:].view(M, N), ss[0:1], a_mn=True,
+                       b_mn=True)
+
+
+@pytest.mark.parametrize("precise", [False, True])
+def test_reg_cross_is_the_inner_product_of_weight_gradient_and_weights(precise):
+    """<X^T dL, w> = sum dL * (X w): evc_reg_cross against the explicit weight gradient (f64)."""
+    from efficientvideoclassification_youtube8m_b200 import ops
+    B, S, N = 48, 256, 1412
+    g = torch.Generator(device="cpu").manual_seed(5)
+    X = torch.randn(B, S, generator=g).to(torch.bfloat16).cuda()
+    W = (torch.randn(S, N, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ld = ops.pad8(N, 64)
+    dl = torch.zeros(B, ld, dtype=torch.bfloat16, device="cuda")
+    dl[:, :N] = (torch.randn(B, N, generator=g) * 1e-2).to(torch.bfloat16).cuda()
+    dl_lo = None
+    if precise:
+        dl_lo = torch.zeros(B, ld, dtype=torch.bfloat16, device="cuda")
+        dl_lo[:, :N] = (torch.randn(B, N, generator=g) * 1e-4).to(torch.bfloat16).cuda()
+    logits = (X.double() @ W.double() + bias.double()).float().contiguous()
+    out = torch.zeros(1, device="cuda")
+    ops.reg_cross(logits, logits.stride(0), dl, ld, bias, B, N, out, dl_lo)
+    d = dl[:, :N].double() + (dl_lo[:, :N].double() if precise else 0.0)
+    want = ((X.double().t() @ d) * W.double()).sum().item()
+    assert abs(out.item() - want) <= 1e-4 * abs(want) + 1e-6, (out.item(), want)
+
+
+def test_clip_adam_fused_norm_parts_equal_the_sumsq_pass():
+    """|g + wd w|^2 assembled from sum g^2, <g, w> and sum w^2 gives the update of the sumsq pass; wsq_out receives
+    the squared norm of the updated weights."""
+    from efficientvideoclassification_youtube8m_b200 import ops
+    n, cols = 64 * 1024, 1024
+    g0 = torch.Generator(device="cpu").manual_seed(9)
+    w = torch.randn(n, generator=g0).cuda()
+    g = (torch.randn(n, generator=g0) * 0.05).cuda()
+    wd, clip = 0.3, 1.0          # a weight decay large enough for every norm term to matter
+    lr_t = torch.tensor([1e-3], device="cuda")
+
+    def run(fused):
+        ww, m, v = w.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        sh = torch.zeros(n // cols, cols, dtype=torch.bfloat16, device="cuda")
+        ns, wsq_out = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+        if fused:
+            parts = torch.stack([(g * g).sum(), (g * w).sum(), (w * w).sum()]).float().contiguous()
+            ops.clip_adam(ww, g, m, v, ns, clip, wd, lr_t, 0.9, 0.999, 1e-8, sh, cols, cols,
+                          normsq_fused=parts[0:1], reg_cross=parts[1:2], reg_wsq=parts[2:3], wsq_out=wsq_out)
+        else:
+            ops.sumsq(g, w, wd, ns)
+            ops.clip_adam(ww, g, m, v, ns, clip, wd, lr_t, 0.9, 0.999, 1e-8, sh, cols, cols)
+        torch.cuda.synchronize()
+        return ww, m, v, sh, wsq_out
+
+    a, b = run(False), run(True)
+    for x, y in zip(a[:3], b[:3]):
+        assert (x - y).abs().max().item() <= 1e-6 * max(1.0, x.abs().max().item())
+    assert (a[3].float() - b[3].float()).abs().max().item() <= 2 ** -7 * a[3].float().abs().max().item()
+    want = b[0].double().pow(2).sum().item()
+    assert abs(b[4].item() - want) <= 1e-5 * want

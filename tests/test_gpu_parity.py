@@ -389,3 +389,85 @@ def test_stream_schedules_equal_the_single_stream_step(mode, monkeypatch):
                 frac = (d > 1e-6).float().mean().item()
                 frac0 = ((ma.w[n] - ma2.w[n]).abs() > 1e-6).float().mean().item()
                 assert frac <= 20 * frac0 + 0.02, (n, frac, frac0)
+
+
+def test_norms_from_the_producers_equal_the_sumsq_pass(monkeypatch):
+    """The default single-GPU step takes the clipped gradient norms in the weight-gradient GEMM epilogues (+ <g, w> from
+    the logits, sum w^2 from the previous clip+Adam launch); EVC_FUSED_NORMS=0 runs the sumsq pass over g and w
+    instead.  (a) on the same gradients the assembled norm equals sum (g + wd w)^2 of every matrix; (b) the
+    regulariser bookkeeping (sum w^2 before / after the update, also after weights were set from outside);
+    (c) both modes train alike (a regularisation penalty large enough for the wd terms to matter)."""
+    from efficientvideoclassification_youtube8m_b200.params import ModelConfig
+    from efficientvideoclassification_youtube8m_b200.steps import TeacherStudentTrainer, _as_u8
+    from oracle import hlstm_oracle as O
+    cfg = ModelConfig(**SMALL)
+    B, penalty = 16, 3e6
+    wd = penalty * cfg.l2_penalty
+    x, nf, lab = O.synthetic_batch(B, seed=11, num_features=cfg.feature_size, vocab_size=cfg.vocab_size, stress=True)
+    xd, nfd, labd = torch.from_numpy(x).cuda(), torch.from_numpy(nf).cuda(), torch.from_numpy(lab).cuda()
+
+    def make(fused):
+        monkeypatch.setenv("EVC_FUSED_NORMS", "1" if fused else "0")
+        tr = TeacherStudentTrainer(cfg, batch_size=B, lstm_gain=2.0, regularization_penalty=penalty,
+                                   clip_gradient_norm=0.05)
+        assert tr.teacher.fused_norms() == fused
+        return tr
+
+    # (a), (b)
+    tr = make(True)
+    for rnd in range(2):
+        if rnd == 1:             # weights set from outside: sum w^2 has to be taken again
+            for p in (tr.teacher, tr.student):
+                p.w[p.gates_w].mul_(1.5)
+                p.refresh_shadows()
+                assert not p._wsq_valid
+        tr.forward_backward(xd, nfd, _as_u8(labd))
+        torch.cuda.synchronize()
+        before = {}
+        for p in (tr.teacher, tr.student):
+            assert p._fused_ready == {0, 2, 4, 6, 8, 9}
+            aux = p.norm_aux.cpu().double()
+            for i in sorted(p._fused_ready):
+                n = p.names[i]
+                g, w = p.g[n].double(), p.w[n].double()
+                reg = n in (p.gates_w, p.experts_w)
+                want = ((g + wd * w) ** 2).sum().item() if reg else (g ** 2).sum().item()
+                got = aux[i, 0].item()
+                if reg:
+                    assert abs(aux[i, 1].item() - (g * w).sum().item()) <= 2e-3 * (g.norm() * w.norm()).item(), n
+                    got += 2 * wd * aux[i, 1].item() + wd * wd * (w ** 2).sum().item()
+                assert abs(got - want) <= 2e-5 * want, (n, got, want)
+            before[p.scope] = [(p.w[n].double() ** 2).sum().item() for n in (p.gates_w, p.experts_w)]
+        tr.apply_gradients()
+        torch.cuda.synchronize()
+        for p in (tr.teacher, tr.student):
+            assert p._wsq_valid and not p._fused_ready
+            for k, n in enumerate((p.gates_w, p.experts_w)):
+                i = p.names.index(n)
+                assert abs(p.wsq[i].item() - before[p.scope][k]) <= 1e-5 * before[p.scope][k]
+                after = (p.w[n].double() ** 2).sum().item()
+                assert abs(p.wsq_next[i].item() - after) <= 1e-5 * after
+
+    # (c)
+    def run(fused):
+        tr = make(fused)
+        out = []
+        for it in range(4):
+            tr.step(xd, nfd, labd)
+            out.append(tr.fetch())
+        torch.cuda.synchronize()
+        return tr, out
+
+    a, la = run(False)
+    b, lb = run(True)
+    for it in range(4):
+        for k in ("teacher_loss", "student_loss", "teacher_reg", "student_reg"):
+            assert abs(la[it][k] - lb[it][k]) <= 1e-4 * abs(la[it][k]) + 1e-7, (it, k, la[it][k], lb[it][k])
+    assert la[0]["teacher_reg"] > 0
+    for pa, pb in ((a.teacher, b.teacher), (a.student, b.student)):
+        for n in pa.names:
+            # Adam's update is nearly invariant to the clip scale (and flips with the sign of near-zero gradient
+            # elements, which the atomically accumulated split-K sums perturb from run to run); its first moment is
+            # linear in the scale
+            dm = (pa.m[n] - pb.m[n]).norm().item()
+            assert dm <= 2e-3 * pa.m[n].norm().item() + 1e-12, (n, dm, pa.m[n].norm().item())
