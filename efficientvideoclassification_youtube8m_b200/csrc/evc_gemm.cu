@@ -180,12 +180,22 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
   if (split_k < 1) split_k = 1;
   if ((split_k > 1 || accumulate) && c_bf16) return set_error(EVC_ERR_ARG, "gemm: split-K/accumulate needs f32 C");
   int bn = force_bn ? force_bn : ((N > 128) ? 256 : 128);
-  // weight-streaming regime (few rows, wide N: the MoE logits GEMMs, 256 x 9432 x 4096): 128 x 256 tiles give fewer
-  // work items than SMs (74 of 148) and stream the weights at a fraction of the HBM rate; 128-wide tiles fill the chip
-  if (!force_bn && bn == 256 && split_k <= 1 && M <= 2 * BM && K <= 8192 &&
-      static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 256) < num_sms() &&
-      static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 128) > static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 256))
-    bn = 128;
+  // weight-streaming regime (few rows, wide N: the MoE logits GEMMs, 256 x 9432 / 14148 x 4096): 128 x 256 tiles give
+  // fewer work items than SMs (experts: 74 CTAs of 148) and stream the weights at a fraction of the HBM rate; 128-wide
+  // tiles fill the chip -- as long as they still fit ONE round over the clusters (experts: 74 pair tiles, 33 vs 37 us;
+  // gates: 111 pair tiles = two rounds, the second half empty: 52 vs 41 us with 256-wide tiles, measured on B200,
+  // profiles/r02_exp_moe_gemm.txt)
+  static int ws128 = -1;   // EVC_WS128=0: keep 256-wide tiles in the weight-streaming regime; 2: the round-2 rule
+  if (ws128 < 0) {         // without the one-round condition (A/B experiments)
+    const char* e = getenv("EVC_WS128");
+    ws128 = e ? atoi(e) : 1;
+  }
+  if (ws128 && !force_bn && bn == 256 && split_k <= 1 && M <= 2 * BM && K <= 8192) {
+    const long long tm = ceil_div(M, BM), cl = tm >= 2 ? num_sms() / kCluster : num_sms();
+    const long long w256 = ceil_div(static_cast<int>(tm), tm >= 2 ? kCluster : 1) * static_cast<long long>(ceil_div(N, 256));
+    const long long w128 = ceil_div(static_cast<int>(tm), tm >= 2 ? kCluster : 1) * static_cast<long long>(ceil_div(N, 128));
+    if (w256 < cl && w128 > w256 && (ws128 == 2 || (w128 + cl - 1) / cl <= (w256 + cl - 1) / cl)) bn = 128;
+  }
   GemmArgs g = {};
   g.M = M; g.N = N;
   g.tiles_m = ceil_div(M, BM);

@@ -339,9 +339,14 @@ class HLstmEngine:
         if not dstate_preset:
             ops.fill_f32(self.dstate, 0.0)
         lo = p.shadow_lo.get if self.precise else (lambda n: None)
-        ops.gemm(self.dG, p.shadow[p.gates_w], B, S, self.ldg, self.dstate, split_k=8, accumulate=True,
+        # split-K so that the work items fill ONE round over the CTA pairs (B = 256, S = 4096: 16 pair tiles x 4 splits
+        # on 74 pairs; 8 splits took a second, partly empty round: 47 -> 45 us and 39 -> 35 us, profiles/r02_exp_moe_gemm.txt)
+        tm, tn = -(-B // 128), -(-S // 256)
+        slots = 74 if tm >= 2 else 148
+        sk = max(1, min(8, slots // (-(-tm // 2) * tn if tm >= 2 else tn)))
+        ops.gemm(self.dG, p.shadow[p.gates_w], B, S, self.ldg, self.dstate, split_k=sk, accumulate=True,
                  A_lo=self.dG_lo, B_lo=lo(p.gates_w))
-        ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=8, accumulate=True,
+        ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=sk, accumulate=True,
                  A_lo=self.dE_lo, B_lo=lo(p.experts_w))
         if p.fused_norms():
             # the two matrices' |g|^2 from the GEMM epilogues and <g, w> from the logits (the regulariser's
