@@ -28,7 +28,7 @@ SIGNATURES = {
     "evc_random_uniform": [C.c_ulonglong, C.c_ulonglong, P, L, P],
     "evc_gemm_bf16": [P, I, L, P, I, L, I, I, I, P, I, L, P, I, I, P],
     "evc_gemm_bf16x2": [P, P, I, L, P, P, I, L, I, I, I, P, I, L, P, I, I, P],
-    "evc_gemm_bf16_sumsq": [P, P, I, L, P, P, I, L, I, I, I, P, L, P, P],
+    "evc_gemm_bf16_wgrad": [P, P, I, L, P, P, I, L, I, I, I, P, L, F, P, P],
     "evc_lstm_seq_fwd": [P, L, I, P, P, I, I, I, P, P, P, P, P, L, P],
     "evc_lstm_seq_fwd_steps": [P, L, I, P, P, I, I, I, I, I, P, P, P, P, P, L, P, P, P, P, P],
     "evc_lstm_workspace_bytes": [I, I, I, I],

@@ -171,7 +171,8 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
                       int K, void* C, int c_bf16, long long ldc, const float* bias, int split_k, int accumulate,
                       cudaStream_t stream, int force_bn = 0, long long split_stride = 0, int* splits_out = nullptr,
                       const void* A2 = nullptr, int K1 = 0, const void* A_lo = nullptr, const void* B_lo = nullptr,
-                      const void* A2_lo = nullptr, bool stream_k = false, float* sumsq_out = nullptr) {
+                      const void* A2_lo = nullptr, bool stream_k = false, float* sumsq_out = nullptr,
+                      float alpha = 1.f) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(EVC_ERR_ARG, "gemm: empty problem");
   // split-bf16 "precise" product: both residual planes or none (same shapes / pitches as the hi planes)
   const bool x2 = A_lo != nullptr || B_lo != nullptr;
@@ -273,11 +274,12 @@ static int gemm_store(const void* A, int a_mn, long long lda, const void* B, int
     g.tma_store = 1;
     g.split_rows = static_cast<int>(slab_rows);
   }
-  if (sumsq_out != nullptr) {
-    // the sum of squares is taken where the epilogue holds the final f32 values: plain TMA-store launches only
+  if (sumsq_out != nullptr || alpha != 1.f) {
+    // the scale and the sum of squares are applied where the epilogue holds the final f32 values: plain TMA stores only
     if (!g.tma_store || c_bf16 || g.split_k > 1 || split_stride != 0)
-      return set_error(EVC_ERR_ARG, "gemm: sumsq_out needs a plain f32 store into a 16-byte aligned C (no split-K)");
+      return set_error(EVC_ERR_ARG, "gemm: alpha / sumsq_out need a plain f32 store into a 16-byte aligned C (no split-K)");
     g.sumsq_out = sumsq_out;
+    g.alpha_m1 = alpha - 1.f;
   }
 #define EVC_DISPATCH(AM, BMN)                                                                    \
   if (a_mn == AM && b_mn == BMN) {                                                                \
@@ -320,12 +322,12 @@ extern "C" int evc_gemm_bf16x2(const void* A, const void* A_lo, int a_mn_major, 
                     static_cast<cudaStream_t>(stream), 0, 0, nullptr, nullptr, 0, A_lo, B_lo);
 }
 
-extern "C" int evc_gemm_bf16_sumsq(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B,
+extern "C" int evc_gemm_bf16_wgrad(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B,
                                    const void* B_lo, int b_mn_major, long long ldb, int M, int N, int K, float* C,
-                                   long long ldc, float* sumsq_out, void* stream) {
-  if (sumsq_out == nullptr) return set_error(EVC_ERR_ARG, "gemm_bf16_sumsq: sumsq_out required");
+                                   long long ldc, float alpha, float* sumsq_out, void* stream) {
   return gemm_store(A, a_mn_major, lda, B, b_mn_major, ldb, M, N, K, C, 0, ldc, nullptr, 1, 0,
-                    static_cast<cudaStream_t>(stream), 0, 0, nullptr, nullptr, 0, A_lo, B_lo, nullptr, false, sumsq_out);
+                    static_cast<cudaStream_t>(stream), 0, 0, nullptr, nullptr, 0, A_lo, B_lo, nullptr, false, sumsq_out,
+                    alpha);
 }
 
 // ------------------------------------------------------------------ BasicLSTM layer, forward over T steps

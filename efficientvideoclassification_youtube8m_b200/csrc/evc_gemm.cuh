@@ -67,6 +67,8 @@ struct GemmArgs {
   int tma_store;       // 1: C is written with TMA bulk stores through tensor map tmC (row offset ks*split_rows)
   int split_rows;      // rows between partial slabs in tmC's row coordinate
   const float* bias;   // [N] or null
+  float alpha_m1;      // plain f32 TMA stores write (1 + alpha_m1) * acc (0 everywhere but the data-parallel weight-gradient
+                       // GEMM over the gathered batch, which averages over the ranks: alpha = 1 / world)
   float* sumsq_out;    // null, or: *sumsq_out += sum of the squares of the f32 C this launch stores (plain stores only) --
                        // the per-variable gradient norm of slim's clip_gradient_norms, taken where the weight
                        // gradient is produced instead of by a second pass over it
@@ -462,6 +464,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (col0 + j < args.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(args.bias + col0 + j));
+              }
+              if (args.alpha_m1 != 0.f) {
+                const float alpha = 1.f + args.alpha_m1;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
               }
               if (args.sumsq_out != nullptr && row_ok) {
                 // (columns past N hold exact zeros: TMA zero-fills the out-of-bounds part of the B tile)

@@ -83,6 +83,7 @@ class HLstmEngine:
         self.training = training
         self.precise = bool(getattr(params, "precise", False))
         self.overlap = overlap_mode()
+        self._dp_all, self._cls_stream, self._cls_done, self._cls_pending = None, None, None, False
         self._fused_norms = False    # inside lstm_backward: weight-gradient GEMMs also leave |dW|^2 (params.norm_aux)
         self._side: Optional[torch.cuda.Stream] = None
         self._events = []
@@ -303,9 +304,9 @@ class HLstmEngine:
         if self._fused_norms:
             # |dW|^2 accumulated by the two GEMMs' epilogues (the clip of slim's train op is per variable)
             ss = p.norm_aux[(level * 2 + cell) * 2, 0:1]
-            ops.gemm_sumsq(x2d, dz, Kx, 4 * H, R, gW[:Kx], ss, a_mn=True, b_mn=True, lda=Kx, ldc=4 * H,
+            ops.gemm_wgrad(x2d, dz, Kx, 4 * H, R, gW[:Kx], ss, a_mn=True, b_mn=True, lda=Kx, ldc=4 * H,
                            A_lo=x2d_lo, B_lo=dz_lo)
-            ops.gemm_sumsq(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], ss, a_mn=True, b_mn=True, lda=H,
+            ops.gemm_wgrad(layer.h_all.view(-1, H), dz, H, 4 * H, R, gW[Kx:], ss, a_mn=True, b_mn=True, lda=H,
                            ldc=4 * H, A_lo=h_lo, B_lo=dz_lo)
             return
         ops.gemm(x2d, dz, Kx, 4 * H, R, gW[:Kx], a_mn=True, b_mn=True, lda=Kx, ldc=4 * H, A_lo=x2d_lo, B_lo=dz_lo)
@@ -328,14 +329,17 @@ class HLstmEngine:
         self.lstm_backward()
 
     def classifier_backward(self, dP: Optional[torch.Tensor], dstate_preset: bool = False,
-                            logits_done: bool = False) -> None:
+                            logits_done: bool = False, dp=None) -> None:
         """MoE backward: weight gradients into params.g, d(state) accumulated into self.dstate.
-        logits_done: self.dG/self.dE were already produced by classifier_loss_fused."""
+        logits_done: self.dG/self.dE were already produced by classifier_loss_fused.
+        dp = (rank, world, group): sharded data parallelism -- see `_classifier_wgrad_gathered`; the two weight
+        gradients are then complete (averaged, this rank's row block only) after `wait_classifier_wgrad()`."""
         p, cfg = self.p, self.cfg
         S, V, M, B = cfg.state_size, cfg.vocab_size, cfg.num_mixtures, self.B
         if not logits_done:
             ops.moe_mix_bwd(self.G, self.ldg, self.E, self.lde, dP, B, V, M, self.dG, self.lddg, self.dE, self.ldde,
                             self.dG_lo, self.dE_lo)
+        gathers = self._classifier_gather(dp) if dp is not None else None
         if not dstate_preset:
             ops.fill_f32(self.dstate, 0.0)
         lo = p.shadow_lo.get if self.precise else (lambda n: None)
@@ -348,13 +352,15 @@ class HLstmEngine:
                  A_lo=self.dG_lo, B_lo=lo(p.gates_w))
         ops.gemm(self.dE, p.shadow[p.experts_w], B, S, self.lde, self.dstate, split_k=sk, accumulate=True,
                  A_lo=self.dE_lo, B_lo=lo(p.experts_w))
-        if p.fused_norms():
+        if dp is not None:
+            self._classifier_wgrad_gathered(dp, gathers)
+        elif p.fused_norms():
             # the two matrices' |g|^2 from the GEMM epilogues and <g, w> from the logits (the regulariser's
             # gradient wd*w enters the clipped norm, train.py:324-334): no sumsq pass over g and w in the optimizer
             p.begin_fused_norms(8, 11)
-            ops.gemm_sumsq(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], p.norm_aux[8, 0:1], a_mn=True,
+            ops.gemm_wgrad(self.state_bf16, self.dG, S, self.ldg, B, p.g[p.gates_w], p.norm_aux[8, 0:1], a_mn=True,
                            b_mn=True, A_lo=self.state_lo, B_lo=self.dG_lo)
-            ops.gemm_sumsq(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], p.norm_aux[9, 0:1], a_mn=True,
+            ops.gemm_wgrad(self.state_bf16, self.dE, S, self.lde, B, p.g[p.experts_w], p.norm_aux[9, 0:1], a_mn=True,
                            b_mn=True, A_lo=self.state_lo, B_lo=self.dE_lo)
             ops.reg_cross(self.G, self.G.stride(0), self.dG, self.lddg, None, B, self.ldg, p.norm_aux[8, 1:2],
                           self.dG_lo)
@@ -371,6 +377,55 @@ class HLstmEngine:
         ops.colsum_bf16(self.dE, B, self.lde, self.ldde, gbe)
         if self.precise:
             ops.colsum_bf16(self.dE_lo, B, self.lde, self.ldde, gbe)      # accumulates: hi + lo
+
+    # ---- sharded data parallelism: the classifier's weight gradients without a gradient collective.
+    # g = X^T dL is a rank-B product (X = the final state [B, S], dL = gradient w.r.t. the logits [B, N], both bf16 as
+    # the weight-gradient GEMM reads them), so the average over ranks (1/world) sum_r X_r^T dL_r is ONE contraction over
+    # the gathered batch: every rank all-gathers X and dL (B x (S + 3 V M) bf16 = 9 MB per rank instead of reduce-
+    # scattering 386 MB of f32 gradients per model) and computes only the row block of g its optimizer shard owns --
+    # the FLOPs of the local weight-gradient GEMM, 1/world of its store traffic, f32 accumulation over all world x B
+    # rows inside one GEMM.  Same averaged gradient as reduce_scatter(AVG) of the per-rank products.
+    def _classifier_gather(self, dp):
+        import torch.distributed as dist
+        rank, world, group = dp
+        srcs = [self.state_bf16, self.dG, self.dE]
+        if self.precise:
+            srcs += [self.state_lo, self.dG_lo, self.dE_lo]
+        if self._dp_all is None or self._dp_all[0].shape[0] != world * self.B:
+            self._dp_all = [torch.empty(world * self.B, t.shape[1], dtype=t.dtype, device=t.device) for t in srcs]
+        return [dist.all_gather_into_tensor(dst, src, group=group, async_op=True)
+                for dst, src in zip(self._dp_all, srcs)]
+
+    def _classifier_wgrad_gathered(self, dp, gathers) -> None:
+        """On a stream of its own (the gathers must not stall the LSTM backward that follows on the caller's stream);
+        `wait_classifier_wgrad` joins it."""
+        rank, world, group = dp
+        p, cfg = self.p, self.cfg
+        S, KB = cfg.state_size, world * self.B
+        if self._cls_stream is None:
+            self._cls_stream = torch.cuda.Stream(device=p.device)
+            self._cls_done = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._cls_stream.wait_stream(main)
+        with torch.cuda.stream(self._cls_stream):
+            for w in gathers:
+                w.wait()
+            X, dG, dE = self._dp_all[:3]
+            Xl, dGl, dEl = self._dp_all[3:] if self.precise else (None, None, None)
+            r0, r1 = p.row_block(p.gates_w, rank, world)
+            ops.gemm_wgrad(X[:, r0:r1], dG, r1 - r0, self.ldg, KB, p.g[p.gates_w][r0:r1], None, a_mn=True, b_mn=True,
+                           alpha=1.0 / world, A_lo=Xl[:, r0:r1] if Xl is not None else None, B_lo=dGl)
+            r0, r1 = p.row_block(p.experts_w, rank, world)
+            ops.gemm_wgrad(X[:, r0:r1], dE, r1 - r0, self.lde, KB, p.g[p.experts_w][r0:r1], None, a_mn=True, b_mn=True,
+                           alpha=1.0 / world, A_lo=Xl[:, r0:r1] if Xl is not None else None, B_lo=dEl)
+            self._cls_done.record(self._cls_stream)
+        self._cls_pending = True
+
+    def wait_classifier_wgrad(self) -> None:
+        """Make the current stream wait for the gathered-batch weight gradients of the classifier (no-op otherwise)."""
+        if self._cls_pending:
+            torch.cuda.current_stream().wait_event(self._cls_done)
+            self._cls_pending = False
 
     def lstm_backward(self) -> None:
         """Backward of both LSTM levels given self.dstate = dLoss/d(final state)."""

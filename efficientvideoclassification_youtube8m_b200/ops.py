@@ -48,15 +48,15 @@ def gemm(A, B, M, N, K, out, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=Non
     return out
 
 
-def gemm_sumsq(A, B, M, N, K, out, sumsq_out, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, A_lo=None,
-               B_lo=None):
-    """Weight-gradient GEMM: out[M,N] (f32) = A @ B and sumsq_out[0] += sum(out^2) from the epilogue."""
+def gemm_wgrad(A, B, M, N, K, out, sumsq_out=None, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, A_lo=None,
+               B_lo=None, alpha=1.0):
+    """Weight-gradient GEMM: out[M,N] (f32) = alpha * A @ B and, if given, sumsq_out[0] += sum(out^2) from the epilogue."""
     lda = lda if lda is not None else A.stride(0)
     ldb = ldb if ldb is not None else B.stride(0)
     ldc = ldc if ldc is not None else out.stride(0)
-    assert out.dtype == torch.float32 and sumsq_out.dtype == torch.float32
-    check(lib.evc_gemm_bf16_sumsq(ptr(A), ptr(A_lo), int(a_mn), lda, ptr(B), ptr(B_lo), int(b_mn), ldb, M, N, K,
-                                  ptr(out), ldc, ptr(sumsq_out), stream()), "evc_gemm_bf16_sumsq")
+    assert out.dtype == torch.float32 and (sumsq_out is None or sumsq_out.dtype == torch.float32)
+    check(lib.evc_gemm_bf16_wgrad(ptr(A), ptr(A_lo), int(a_mn), lda, ptr(B), ptr(B_lo), int(b_mn), ldb, M, N, K,
+                                  ptr(out), ldc, float(alpha), ptr(sumsq_out), stream()), "evc_gemm_bf16_wgrad")
     return out
 
 

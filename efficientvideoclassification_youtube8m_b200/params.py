@@ -99,7 +99,7 @@ class HLstmParams:
         self.normsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
         self.wsq = torch.zeros(len(self.names), dtype=torch.float32, device=self.device)
         # Norms taken where the gradients are produced (one process, CUDA): the weight-gradient GEMMs leave sum g^2 of
-        # their matrix in norm_aux[i, 0] (evc_gemm_bf16_sumsq), evc_reg_cross leaves <g, w> of the two regularised
+        # their matrix in norm_aux[i, 0] (evc_gemm_bf16_wgrad), evc_reg_cross leaves <g, w> of the two regularised
         # matrices in norm_aux[i, 1], and the clip+Adam kernel accumulates sum w^2 of the weights it writes into
         # wsq_next -- so the optimizer needs no sumsq pass over the matrices (`begin_fused_norms`, `apply_gradients`).
         self.norm_aux = torch.zeros(len(self.names), 2, dtype=torch.float32, device=self.device)

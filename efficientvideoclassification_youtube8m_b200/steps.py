@@ -145,6 +145,15 @@ class _Base:
             dist.all_reduce(buf, op=dist.ReduceOp.SUM)
             buf.div_(n)
 
+    def _dp(self):
+        """(rank, world, group) for `HLstmEngine.classifier_backward` in the sharded data-parallel mode: the
+        classifier's weight gradients come from one contraction over the all-gathered batch (9 MB of bf16 operands
+        on the wire per rank and model instead of a 386 MB f32 reduce-scatter); EVC_DP_GATHER=0 keeps the
+        reduce-scatter for them too (A/B)."""
+        if not self._sharded() or (self._dp_ablate & 1) or os.environ.get("EVC_DP_GATHER", "1") == "0":
+            return None
+        return dist.get_rank(), self._world(), None
+
     def _reduce_grads(self, params, names):
         """Average the gradients of `names` over the ranks: whole-buffer all-reduce slices in the replicated
         mode, per-matrix reduce-scatter (owner keeps the average of its row block) + bias all-reduce in the
@@ -158,7 +167,10 @@ class _Base:
             self._allreduce(params, lo, hi)
             return
         rank = dist.get_rank()
+        gathered = (params.gates_w, params.experts_w) if self._dp() is not None else ()
         for x in names:
+            if x in gathered:        # already averaged: computed from the gathered batch (engine._classifier_wgrad_gathered)
+                continue
             g = params.g[x]
             if g.dim() == 2:
                 r0, r1 = params.row_block(x, rank, n)
@@ -167,9 +179,15 @@ class _Base:
                 w = dist.all_reduce(g, op=dist.ReduceOp.AVG, async_op=True)
             self._pending.append((params, w))
 
+    def _wait_classifier_wgrad(self, params):
+        for eng in (getattr(self, "t_eng", None), getattr(self, "s_eng", None)):
+            if eng is not None and eng.p is params:
+                eng.wait_classifier_wgrad()
+
     def _apply(self, params):
         """clip + Adam for one parameter set (after its gradient collectives have completed)."""
         self._finish_allreduce(params)
+        self._wait_classifier_wgrad(params)
         n = self._world()
         if n > 1 and self.shard_optimizer and dist.get_backend() == "nccl":
             self._gathers.setdefault(id(params), []).extend(
@@ -214,6 +232,8 @@ class _Base:
 
     def _apply_range(self, params, first, last):
         """clip + Adam of names[first:last] on the current stream once their gradient collectives are complete."""
+        if last is None or last > 8:
+            self._wait_classifier_wgrad(params)
         if self._sharded():
             self._finish_allreduce(params)      # (only this range's collectives have been issued so far)
             self._gathers.setdefault(id(params), []).extend(
@@ -309,18 +329,20 @@ class TeacherStudentTrainer(_Base):
             s.forward(raw, idx, True, self.nf_student, num_frames, mix=False)
         t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
         self._teacher_ready.record(main)             # t.state and t.pred are final
+        # (the teacher's classifier backward is issued before the student's: collectives of one communicator run in
+        # issue order, and the teacher's operands are final first)
+        t.classifier_backward(None, logits_done=True, dp=self._dp())
+        self._reduce_grads(self.teacher, self.teacher.names[8:])
+        if fuse_optimizer:
+            self._apply_classifier_early(self.teacher)
         with torch.cuda.stream(side):
             side.wait_event(self._teacher_ready)
             ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
             s.classifier_loss_fused(labels_u8, t.pred, 1.0 / B, 1.0, self.rows[1], self.rows[2])
-            s.classifier_backward(None, dstate_preset=True, logits_done=True)
+            s.classifier_backward(None, dstate_preset=True, logits_done=True, dp=self._dp())
             self._reduce_grads(self.student, self.student.names[8:])
             if fuse_optimizer:
                 self._apply_classifier_early(self.student)
-        t.classifier_backward(None, logits_done=True)
-        self._reduce_grads(self.teacher, self.teacher.names[8:])
-        if fuse_optimizer:
-            self._apply_classifier_early(self.teacher)
         t.lstm_backward()
         self._reduce_grads(self.teacher, self.teacher.names[:8])
         ops.reduce_rows(self.rows[0], 1.0 / B, self.losses[0:1])
@@ -340,6 +362,8 @@ class TeacherStudentTrainer(_Base):
         self._forward_backward(raw, num_frames, labels_u8, u=u)
         if self.student_stream is not None:
             torch.cuda.current_stream().wait_stream(self.student_stream)
+        self.t_eng.wait_classifier_wgrad()
+        self.s_eng.wait_classifier_wgrad()
 
     def _forward_backward(self, raw, num_frames, labels_u8, fuse_optimizer=False, u=None):
         if self.student_stream is not None:
@@ -356,7 +380,7 @@ class TeacherStudentTrainer(_Base):
         # teacher loss = penalty*reg + CE (train.py:297-324); reg enters through the optimizer's wd term.
         # One launch: mixture, CE rows and the gradients w.r.t. the logits.
         t.classifier_loss_fused(labels_u8, None, 1.0 / B, 0.0, self.rows[0], None)
-        t.classifier_backward(None, logits_done=True)
+        t.classifier_backward(None, logits_done=True, dp=self._dp())
         self._reduce_grads(self.teacher, self.teacher.names[8:])   # classifier gradients travel during the LSTM backward
         t.lstm_backward()
         self._reduce_grads(self.teacher, self.teacher.names[:8])
@@ -364,7 +388,7 @@ class TeacherStudentTrainer(_Base):
         # constants for the student's backward (F9)
         ops.rep_loss(t.state, s.state, 4.0 / B, self.rows[3], s.dstate)
         s.classifier_loss_fused(labels_u8, t.pred, 1.0 / B, 1.0, self.rows[1], self.rows[2])
-        s.classifier_backward(None, dstate_preset=True, logits_done=True)
+        s.classifier_backward(None, dstate_preset=True, logits_done=True, dp=self._dp())
         self._reduce_grads(self.student, self.student.names[8:])
         s.lstm_backward()
         self._reduce_grads(self.student, self.student.names[:8])
@@ -439,7 +463,7 @@ class StudentFinetuneTrainer(_Base):
         idx = self._student_sample(num_frames, u)
         s.forward(model_input_raw, idx, True, self.nf_student, num_frames, mix=False)
         s.classifier_loss_fused(_as_u8(labels), None, 1.0 / B, 0.0, self.rows[0], None)
-        s.classifier_backward(None, logits_done=True)
+        s.classifier_backward(None, logits_done=True, dp=self._dp())
         self._reduce_grads(self.student, self.student.names[8:])
         early = self._early_apply_ok()
         if early:

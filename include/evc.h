@@ -101,12 +101,14 @@ int evc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
 int evc_gemm_bf16x2(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B, const void* B_lo,
                     int b_mn_major, long long ldb, int M, int N, int K, void* C, int c_is_bf16, long long ldc,
                     const float* bias, int split_k, int accumulate, void* stream);
-/* Weight-gradient form: C f32 = A * B stored plainly (no bias, no split-K; A_lo / B_lo nullable residual planes) and
- * sumsq_out[0] += sum of C^2, taken in the epilogue from the accumulators -- the per-variable gradient norm of slim's
- * clip_gradient_norms (train.py:329-334) without a second pass over the gradient.  C must be 16-byte aligned. */
-int evc_gemm_bf16_sumsq(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B, const void* B_lo,
-                        int b_mn_major, long long ldb, int M, int N, int K, float* C, long long ldc, float* sumsq_out,
-                        void* stream);
+/* Weight-gradient form: C f32 = alpha * (A * B), stored plainly (no bias, no split-K; A_lo / B_lo nullable residual
+ * planes), and sumsq_out[0] += sum of C^2 (nullable), taken in the epilogue from the accumulators -- the per-variable
+ * gradient norm of slim's clip_gradient_norms (train.py:329-334) without a second pass over the gradient.  alpha: 1, or
+ * 1/world when the contraction runs over the gathered batch of all data-parallel ranks (the averaged gradient).
+ * C must be 16-byte aligned. */
+int evc_gemm_bf16_wgrad(const void* A, const void* A_lo, int a_mn_major, long long lda, const void* B, const void* B_lo,
+                        int b_mn_major, long long ldb, int M, int N, int K, float* C, long long ldc, float alpha,
+                        float* sumsq_out, void* stream);
 
 /* ---- tf.nn.dynamic_rnn(BasicLSTMCell(H, forget_bias=1.0), x, sequence_length) for ONE cell of
  * the MultiRNNCell stack (frame_level_models.py:221-257, 291-328), all `rows` sequences at once.
@@ -214,7 +216,7 @@ int evc_clip_adam(float* w, const float* g, float* m, float* v, long long n, con
 /* The same update with the squared norm of the regularised gradient assembled from parts taken where they are cheap
  * instead of by an evc_sumsq pass over g and w (slim clip_gradient_norms on g + wd*w, train.py:329-334):
  *   |g + wd*w|^2 = *normsq + *normsq_fused + 2*wd * *reg_cross + wd^2 * *reg_wsq      (the last three nullable)
- * normsq_fused = sum g^2 from the weight-gradient GEMM's epilogue (evc_gemm_bf16_sumsq), reg_cross = <g, w>
+ * normsq_fused = sum g^2 from the weight-gradient GEMM's epilogue (evc_gemm_bf16_wgrad), reg_cross = <g, w>
  * (evc_reg_cross), reg_wsq = sum w^2.  wsq_out (nullable): += sum of the squares of the UPDATED weights, i.e. the
  * next step's reg_wsq and regulariser value (video_level_models.py:428,434). */
 int evc_clip_adam_fused(float* w, const float* g, float* m, float* v, long long n, const float* normsq,

@@ -329,7 +329,7 @@ def test_lstm_cluster_step_matches_slab_path(rows, Kx, H, T, want_ks):
 
 
 @pytest.mark.parametrize("M,N,K,precise", [(1152, 4096, 2560, False), (512, 1412, 256, False), (300, 712, 192, True)])
-def test_gemm_sumsq_epilogue(M, N, K, precise):
+def test_gemm_wgrad_sumsq_epilogue(M, N, K, precise):
     """Weight-gradient form (A and B MN-major): same C as the plain GEMM and sum(C^2) from the epilogue, accumulated
     over two launches into one slot (the x and h parts of one LSTM kernel matrix)."""
     from efficientvideoclassification_youtube8m_b200 import ops
@@ -341,8 +341,8 @@ def test_gemm_sumsq_epilogue(M, N, K, precise):
     ops.gemm(A, B, M, N, K, ref, a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
     out = torch.full((M, N), float("nan"), device="cuda")
     ss = torch.zeros(2, device="cuda")
-    ops.gemm_sumsq(A, B, M, N, K, out, ss[0:1], a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
-    ops.gemm_sumsq(A, B, M, N, K, out, ss[0:1], a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
+    ops.gemm_wgrad(A, B, M, N, K, out, ss[0:1], a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
+    ops.gemm_wgrad(A, B, M, N, K, out, ss[0:1], a_mn=True, b_mn=True, A_lo=A_lo, B_lo=B_lo)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
     want = 2.0 * ref.double().pow(2).sum().item()
@@ -351,7 +351,7 @@ def test_gemm_sumsq_epilogue(M, N, K, precise):
     # rejected before any launch: bf16 C has no sumsq form, unaligned C
     from efficientvideoclassification_youtube8m_b200._lib import EvcError
     with pytest.raises(EvcError):
-        ops.gemm_sumsq(A, B, M, N, K, torch.empty(M * N + 1, device="cuda")[1:].view(M, N), ss[0:1], a_mn=True,
+        ops.gemm_wgrad(A, B, M, N, K, torch.empty(M * N + 1, device="cuda")[1:].view(M, N), ss[0:1], a_mn=True,
                        b_mn=True)
 
 

@@ -33,6 +33,9 @@ def _worker(rank, world, port, shard, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
+    if shard == "rs":          # sharded optimizer with the gradient reduce-scatter for the classifier's matrices too
+        os.environ["EVC_DP_GATHER"] = "0"
+        shard = True
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from oracle import hlstm_oracle as O
@@ -82,8 +85,11 @@ def _oracle_dp(world):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("shard", [True, False])
+@pytest.mark.parametrize("shard", [True, "rs", False])
 def test_two_rank_training_matches_data_parallel_oracle(shard):
+    """shard=True: sharded optimizer, LSTM gradients reduce-scattered, the classifier's weight gradients from one
+    contraction over the all-gathered batch (engine._classifier_wgrad_gathered); "rs": reduce-scatter for all;
+    False: replicated optimizer with all-reduce."""
     import torch.multiprocessing as mp
     world = 2
     with mp.Manager() as m:
