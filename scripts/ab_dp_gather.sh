@@ -3,7 +3,7 @@
 N=${1:-2}
 OUT=gpurun_out/r02_dp_gather_ab_${N}gpu.txt
 : > $OUT
-for g in 1 0 1 0; do
+for g in ${GATHER_ORDER:-1 0 1 0}; do
   EVC_DP_GATHER=$g python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 \
     bench.py --gpus $N --steps 20 --warmup 3 --skip-f32-e2e --skip-tfrecord --skip-configs --skip-infer > gpurun_out/_ab.json 2> gpurun_out/_ab.err
   python - <<PY >> $OUT

@@ -39,7 +39,9 @@ torch.cuda.profiler.start()
 if piece == "bwd":
     t._cell_bwd(b, 0, 1, H, t.len_l1, None, t.dl2_in, 2 * H, t.scr_l1)
 elif piece == "wgrad":
+    t._fused_norms = tr.teacher.fused_norms()      # as inside lstm_backward: |dW|^2 from the GEMM epilogue
     t._cell_wgrad(b, 0, 1, a.h_all[1:].view(-1, H), H)
+    t._fused_norms = False
     t._cell_dx(b, 0, 1, H, t.dx_l1)
 elif piece == "fwd":
     t._cell_fwd(a, t.x, t.R1 * D, D, 0, 0, t.len_l1)
