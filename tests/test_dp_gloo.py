@@ -178,3 +178,44 @@ def test_uneven_shards_keep_ranks_in_step_world2(tmp_path):
     assert all(s[1:] == ((300, 8), (10,)) for r in (0, 1) for s in got[r]["pad"][0])
     ids = got[0]["pad"][1] + got[1]["pad"][1]
     assert len(ids) == 2 * sum(counts) and len(set(ids)) == sum(counts)      # every video, every epoch
+
+
+def _gather_worker(rank, world, port, out):
+    """The identity behind engine._classifier_wgrad_gathered, on the CPU: the reduce-scatter(AVG) row block of the
+    per-rank weight gradients X_r^T dL_r equals (1/world) * X_all[:, r0:r1]^T dL_all over the all-gathered batch, with
+    the row blocks of HLstmParams.row_block."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from efficientvideoclassification_youtube8m_b200.params import HLstmParams
+    B, S, N = 6, 8, 10
+    g = torch.Generator().manual_seed(100 + rank)
+    X = torch.randn(B, S, generator=g, dtype=torch.float64)
+    dL = torch.randn(B, N, generator=g, dtype=torch.float64)
+    # (a) what the reduce-scatter mode leaves on this rank: the average of the local products, own row block
+    local = X.t() @ dL
+    dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    local /= world
+
+    class P:                                   # row_block only reads the shapes
+        shapes = {"w": (S, N)}
+    r0, r1 = HLstmParams.row_block(P, "w", rank, world)
+    # (b) the gathered-batch form: all-gather the operands, one contraction, alpha = 1 / world
+    Xs, dLs = [torch.zeros_like(X) for _ in range(world)], [torch.zeros_like(dL) for _ in range(world)]
+    dist.all_gather(Xs, X)
+    dist.all_gather(dLs, dL)
+    X_all, dL_all = torch.cat(Xs), torch.cat(dLs)
+    mine = (1.0 / world) * (X_all[:, r0:r1].t() @ dL_all)
+    blocks = [None] * world
+    dist.all_gather_object(blocks, (r0, r1))
+    out[rank] = {"ok": bool(torch.allclose(mine, local[r0:r1], rtol=1e-12, atol=1e-12)), "blocks": blocks}
+    dist.destroy_process_group()
+
+
+def test_gathered_batch_weight_gradient_equals_reduce_scatter_world2():
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_gather_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+    assert res[0]["ok"] and res[1]["ok"]
+    assert res[0]["blocks"] == [(0, 4), (4, 8)]          # the row blocks tile the matrix
